@@ -1,0 +1,428 @@
+// Implicit-GEMM contraction kernel for sm_100a: one persistent, warp-specialised kernel that
+// serves every Linear / Conv2d 3x3 / Conv2d 3x3 stride 2 / Conv3d (3,1,1) on the SVD UNet and
+// temporal-VAE path (reference call sites listed in include/wiw.h).
+//
+//   warp 0      TMA producer: per k-iteration one 5-D box load of A (a 128-pixel patch x 64 channels,
+//               shifted by the filter tap; out-of-range = zero padding) and one 2-D box of W
+//   warp 1      MMA issuer: tcgen05.mma cta_group::1 kind::f16, M=128, N=bn, K=16 x4 per stage,
+//               fp32 accumulators in TMEM, double-buffered across tiles
+//   warp 2      TMEM allocator + TMA loader of the epilogue's residual / aux tiles
+//   warps 3-6   epilogue: tcgen05.ld -> (bias, per-row-group table, GEGLU, residual blend) -> fp16
+//               -> swizzled smem -> TMA store (clips partial tiles)
+//
+// Pipelines: smem full/empty ring (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue),
+// residual full/empty ring (loader <-> epilogue), bulk-group ring for the stores.
+#include "wiw_common.cuh"
+#include "../../include/wiw.h"
+
+namespace wiw {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;                    // 64 fp16 = one 128-byte swizzle row
+constexpr int kEpiCols = 32;                   // epilogue chunk: 32 fp16 = 64-byte rows (SWIZZLE_64B)
+constexpr int kEpiChunkBytes = kBlockM * kEpiCols * 2;   // 8 KB
+constexpr int kOutBufs = 3;
+constexpr int kResSlots = 4;
+constexpr int kMaxStages = 8;
+constexpr int kThreads = 7 * 32;
+constexpr int kSmemBudget = 227 * 1024;
+
+struct GemmArgs {
+    int total_tiles, n_tiles, tiles_x, tiles_y;
+    int bx, by, dim_x, dim_y;
+    int bn, stages, num_taps, chunks_per_tap;
+    int out_cols_per_tile, geglu, has_res, has_aux;
+    int tab_div, tab_mod, n_total, tmem_cols;
+    const float* bias;
+    const float* tab;
+    float s_acc, s_res, s_aux;
+    int tap_cbase[9], tap_ox[9], tap_p[9], tap_oy[9];
+};
+
+struct TileCoord {
+    int x0, y0, img, n_tile;
+};
+__device__ __forceinline__ TileCoord decode_tile(const GemmArgs& g, int tile) {
+    TileCoord t;
+    int m_tile = tile / g.n_tiles;
+    t.n_tile = tile - m_tile * g.n_tiles;
+    int tx = m_tile % g.tiles_x;
+    int r = m_tile / g.tiles_x;
+    int ty = r % g.tiles_y;
+    t.img = r / g.tiles_y;
+    t.x0 = tx * g.bx;
+    t.y0 = ty * g.by;
+    return t;
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+                 const __grid_constant__ CUtensorMap tm_out, const __grid_constant__ CUtensorMap tm_res,
+                 const __grid_constant__ CUtensorMap tm_aux, const __grid_constant__ GemmArgs g) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // carve: [stages x (A 16 KB | B bn*128)] [out bufs] [res slots] [aux slots] [barriers]
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t a_bytes = kBlockM * kBlockK * 2;
+    const uint32_t b_bytes = g.bn * kBlockK * 2;
+    const uint32_t stage_bytes = a_bytes + b_bytes;
+    const uint32_t out_base = smem_base + g.stages * stage_bytes;
+    const uint32_t res_base = out_base + kOutBufs * kEpiChunkBytes;
+    const uint32_t aux_base = res_base + (g.has_res ? kResSlots * kEpiChunkBytes : 0);
+    const uint32_t bar_base = aux_base + (g.has_aux ? kResSlots * kEpiChunkBytes : 0);
+    // barrier slots (8 B each)
+    const uint32_t bar_full = bar_base;                         // [kMaxStages]
+    const uint32_t bar_empty = bar_full + 8 * kMaxStages;       // [kMaxStages]
+    const uint32_t bar_tfull = bar_empty + 8 * kMaxStages;      // [2]
+    const uint32_t bar_tempty = bar_tfull + 16;                 // [2]
+    const uint32_t bar_rfull = bar_tempty + 16;                 // [kResSlots]
+    const uint32_t bar_rempty = bar_rfull + 8 * kResSlots;      // [kResSlots]
+    const uint32_t tmem_slot = bar_rempty + 8 * kResSlots;      // uint32
+    uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int k_iters = g.num_taps * g.chunks_per_tap;
+    const bool has_epi_loads = g.has_res || g.has_aux;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tm_a);
+        tma_prefetch_desc(&tm_b);
+        tma_prefetch_desc(&tm_out);
+        if (g.has_res) tma_prefetch_desc(&tm_res);
+        if (g.has_aux) tma_prefetch_desc(&tm_aux);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < g.stages; ++i) {
+            mbar_init(bar_full + 8 * i, 1);
+            mbar_init(bar_empty + 8 * i, 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(bar_tfull + 8 * i, 1);
+            mbar_init(bar_tempty + 8 * i, 128);
+        }
+        for (int i = 0; i < kResSlots; ++i) {
+            mbar_init(bar_rfull + 8 * i, 1);
+            mbar_init(bar_rempty + 8 * i, 128);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) {
+        tmem_alloc(tmem_slot, g.tmem_cols);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+    const uint32_t acc_stride = (g.bn <= 32) ? 32 : (g.bn <= 64 ? 64 : (g.bn <= 128 ? 128 : 256));
+
+    if (warp == 0) {
+        // ================================ TMA producer ================================
+        if (lane == 0) {
+            int s = 0;
+            uint32_t ph = 0;
+            for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
+                const TileCoord t = decode_tile(g, tile);
+                const int n0 = t.n_tile * g.bn;
+                int kcol = 0;
+                for (int tap = 0; tap < g.num_taps; ++tap) {
+                    const int cb = g.tap_cbase[tap], cx = t.x0 + g.tap_ox[tap], cp = g.tap_p[tap], cy = t.y0 + g.tap_oy[tap];
+                    for (int ch = 0; ch < g.chunks_per_tap; ++ch) {
+                        mbar_wait(bar_empty + 8 * s, ph ^ 1);
+                        const uint32_t sa = smem_base + s * stage_bytes;
+                        mbar_expect_tx(bar_full + 8 * s, stage_bytes);
+                        tma_load_5d(sa, &tm_a, bar_full + 8 * s, cb + ch * kBlockK, cx, cp, cy, t.img);
+                        tma_load_2d(sa + a_bytes, &tm_b, bar_full + 8 * s, kcol, n0);
+                        kcol += kBlockK;
+                        if (++s == g.stages) { s = 0; ph ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================================ MMA issuer ================================
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_f16(g.bn);
+            int s = 0;
+            uint32_t ph = 0;
+            int as = 0;
+            uint32_t aph = 0;
+            for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
+                mbar_wait(bar_tempty + 8 * as, aph ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + as * acc_stride;
+                for (int it = 0; it < k_iters; ++it) {
+                    mbar_wait(bar_full + 8 * s, ph);
+                    tc_fence_after();
+                    const uint32_t sa = smem_base + s * stage_bytes;
+                    const uint64_t da = make_desc_sw128(sa);
+                    const uint64_t db = make_desc_sw128(sa + a_bytes);
+#pragma unroll
+                    for (int kk = 0; kk < kBlockK / 16; ++kk) {
+                        // +32 bytes per K=16 step inside the 128-byte swizzle row (units of 16 B)
+                        umma_f16_ss(d_tmem, da + 2 * kk, db + 2 * kk, idesc, (it > 0 || kk > 0) ? 1u : 0u);
+                    }
+                    umma_commit(bar_empty + 8 * s);          // frees the smem stage when the MMAs retire
+                    if (++s == g.stages) { s = 0; ph ^= 1; }
+                }
+                umma_commit(bar_tfull + 8 * as);             // accumulator ready for the epilogue
+                if (++as == 2) { as = 0; aph ^= 1; }
+            }
+        }
+    } else if (warp == 2) {
+        // ================================ epilogue loader ================================
+        if (has_epi_loads && lane == 0) {
+            const int chunks = g.out_cols_per_tile / kEpiCols;
+            const uint32_t bytes = kEpiChunkBytes * ((g.has_res ? 1 : 0) + (g.has_aux ? 1 : 0));
+            int rs = 0;
+            uint32_t rph = 0;
+            for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
+                const TileCoord t = decode_tile(g, tile);
+                const int c0 = t.n_tile * g.out_cols_per_tile;
+                for (int j = 0; j < chunks; ++j) {
+                    mbar_wait(bar_rempty + 8 * rs, rph ^ 1);
+                    mbar_expect_tx(bar_rfull + 8 * rs, bytes);
+                    if (g.has_res) tma_load_4d(res_base + rs * kEpiChunkBytes, &tm_res, bar_rfull + 8 * rs, c0 + j * kEpiCols, t.x0, t.y0, t.img);
+                    if (g.has_aux) tma_load_4d(aux_base + rs * kEpiChunkBytes, &tm_aux, bar_rfull + 8 * rs, c0 + j * kEpiCols, t.x0, t.y0, t.img);
+                    if (++rs == kResSlots) { rs = 0; rph ^= 1; }
+                }
+            }
+        }
+    } else {
+        // ================================ epilogue (warps 3..6) ================================
+        const int q = warp & 3;                        // TMEM lane quadrant this warp may access
+        const int row = q * 32 + lane;                 // row of the 128-row tile == TMEM lane
+        const bool store_leader = (warp == 3 && lane == 0);
+        const int chunks = g.out_cols_per_tile / kEpiCols;
+        const uint32_t sw = (uint32_t(row) >> 1) & 3u;  // SWIZZLE_64B: 16-B chunk index ^= (row>>1)&3
+        const uint32_t row_off = uint32_t(row) * 64u;
+        int as = 0;
+        uint32_t aph = 0;
+        int rs = 0;
+        uint32_t rph = 0;
+        int ob = 0;
+        for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
+            const TileCoord t = decode_tile(g, tile);
+            const int acc_n0 = t.n_tile * g.bn;                       // first GEMM column of this tile
+            const int out_c0 = t.n_tile * g.out_cols_per_tile;        // first output channel
+            const float* tab_row = nullptr;
+            if (g.tab != nullptr) {
+                const int x = t.x0 + (row % g.bx), y = t.y0 + (row / g.bx);
+                long long grow = ((long long)t.img * g.dim_y + y) * g.dim_x + x;
+                if (grow < 0) grow = 0;
+                int gi = int((grow / g.tab_div) % g.tab_mod);
+                tab_row = g.tab + (size_t)gi * g.n_total;
+            }
+            mbar_wait(bar_tfull + 8 * as, aph);
+            tc_fence_after();
+            const uint32_t t_acc = tmem_base + as * acc_stride + (uint32_t(q * 32) << 16);
+            for (int j = 0; j < chunks; ++j) {
+                float v[kEpiCols];
+                {
+                    uint32_t r[kEpiCols];
+                    tmem_ld_32x32b_x32(t_acc + j * kEpiCols, r);
+                    tmem_ld_wait();
+                    const int nb = acc_n0 + j * kEpiCols;
+#pragma unroll
+                    for (int c = 0; c < kEpiCols; ++c) v[c] = __uint_as_float(r[c]);
+                    if (g.bias != nullptr) {
+#pragma unroll
+                        for (int c = 0; c < kEpiCols; c += 4) {
+                            const float4 b4 = __ldg(reinterpret_cast<const float4*>(g.bias + nb + c));
+                            v[c] += b4.x; v[c + 1] += b4.y; v[c + 2] += b4.z; v[c + 3] += b4.w;
+                        }
+                    }
+                    if (tab_row != nullptr) {
+#pragma unroll
+                        for (int c = 0; c < kEpiCols; c += 4) {
+                            const float4 b4 = __ldg(reinterpret_cast<const float4*>(tab_row + nb + c));
+                            v[c] += b4.x; v[c + 1] += b4.y; v[c + 2] += b4.z; v[c + 3] += b4.w;
+                        }
+                    }
+                }
+                if (g.geglu) {
+                    uint32_t r[kEpiCols];
+                    const int half_n = g.bn >> 1;
+                    tmem_ld_32x32b_x32(t_acc + half_n + j * kEpiCols, r);
+                    tmem_ld_wait();
+                    const int nb = acc_n0 + half_n + j * kEpiCols;
+#pragma unroll
+                    for (int c = 0; c < kEpiCols; c += 4) {
+                        const float4 b4 = (g.bias != nullptr) ? __ldg(reinterpret_cast<const float4*>(g.bias + nb + c)) : make_float4(0, 0, 0, 0);
+                        v[c] *= gelu_erf_f(__uint_as_float(r[c]) + b4.x);
+                        v[c + 1] *= gelu_erf_f(__uint_as_float(r[c + 1]) + b4.y);
+                        v[c + 2] *= gelu_erf_f(__uint_as_float(r[c + 2]) + b4.z);
+                        v[c + 3] *= gelu_erf_f(__uint_as_float(r[c + 3]) + b4.w);
+                    }
+                }
+                if (j == chunks - 1) {
+                    // all TMEM reads of this accumulator stage are done: hand it back to the MMA warp
+                    tc_fence_before();
+                    mbar_arrive(bar_tempty + 8 * as);
+                }
+                if (g.s_acc != 1.0f) {
+#pragma unroll
+                    for (int c = 0; c < kEpiCols; ++c) v[c] *= g.s_acc;
+                }
+                if (has_epi_loads) {
+                    mbar_wait(bar_rfull + 8 * rs, rph);
+                    const uint8_t* gen = smem_raw + (res_base - smem_u32(smem_raw));
+                    if (g.has_res) {
+                        const uint8_t* p = gen + rs * kEpiChunkBytes + row_off;
+#pragma unroll
+                        for (int c4 = 0; c4 < 4; ++c4) {
+                            const uint4 u = *reinterpret_cast<const uint4*>(p + ((uint32_t(c4) ^ sw) << 4));
+                            const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const float2 f = __half22float2(h[e]);
+                                v[c4 * 8 + 2 * e] += g.s_res * f.x;
+                                v[c4 * 8 + 2 * e + 1] += g.s_res * f.y;
+                            }
+                        }
+                    }
+                    if (g.has_aux) {
+                        const uint8_t* p = smem_raw + (aux_base - smem_u32(smem_raw)) + rs * kEpiChunkBytes + row_off;
+#pragma unroll
+                        for (int c4 = 0; c4 < 4; ++c4) {
+                            const uint4 u = *reinterpret_cast<const uint4*>(p + ((uint32_t(c4) ^ sw) << 4));
+                            const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const float2 f = __half22float2(h[e]);
+                                v[c4 * 8 + 2 * e] += g.s_aux * f.x;
+                                v[c4 * 8 + 2 * e + 1] += g.s_aux * f.y;
+                            }
+                        }
+                    }
+                    mbar_arrive(bar_rempty + 8 * rs);
+                    if (++rs == kResSlots) { rs = 0; rph ^= 1; }
+                }
+                // fp16 -> swizzled staging buffer `ob`
+                {
+                    uint8_t* p = smem_raw + (out_base - smem_u32(smem_raw)) + ob * kEpiChunkBytes + row_off;
+#pragma unroll
+                    for (int c4 = 0; c4 < 4; ++c4) {
+                        uint4 u;
+                        __half2* h = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) h[e] = __floats2half2_rn(v[c4 * 8 + 2 * e], v[c4 * 8 + 2 * e + 1]);
+                        *reinterpret_cast<uint4*>(p + ((uint32_t(c4) ^ sw) << 4)) = u;
+                    }
+                }
+                fence_proxy_async_smem();
+                // The leader makes sure the store that last used the NEXT buffer has finished reading
+                // it (<= 1 group may stay in flight), so this single barrier both publishes chunk j
+                // and frees the buffer chunk j+1 will write.
+                if (store_leader) tma_store_wait_read<1>();
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (store_leader) {
+                    tma_store_4d(&tm_out, out_base + ob * kEpiChunkBytes, out_c0 + j * kEpiCols, t.x0, t.y0, t.img);
+                    tma_store_commit();
+                }
+                if (++ob == kOutBufs) ob = 0;
+            }
+            if (++as == 2) { as = 0; aph ^= 1; }
+        }
+        if (store_leader) tma_store_wait_all<0>();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, g.tmem_cols);
+    }
+}
+
+// ----------------------------------------------------------------------------- host side
+static int launch_conv_gemm(const wiw_gemm_desc* d, cudaStream_t stream) {
+    WIW_REQUIRE(d != nullptr && d->a && d->w && d->out, "null pointer");
+    WIW_REQUIRE(d->a_stride[0] == 1 && d->out_stride[0] == 1, "channel axis must be contiguous");
+    WIW_REQUIRE(d->bx > 0 && d->by > 0 && d->bx * d->by == kBlockM, "bx*by must be 128");
+    WIW_REQUIRE(d->bn >= 32 && d->bn <= 256 && d->bn % 32 == 0, "bn must be a multiple of 32 in [32,256]");
+    WIW_REQUIRE(!d->geglu || d->bn % 64 == 0, "geglu needs bn % 64 == 0");
+    WIW_REQUIRE(d->n_total % d->bn == 0, "n_total must be a multiple of bn");
+    WIW_REQUIRE(d->num_taps >= 1 && d->num_taps <= 9 && d->chunks_per_tap >= 1, "bad tap spec");
+    WIW_REQUIRE(d->k_total == (int64_t)d->num_taps * d->chunks_per_tap * kBlockK, "k_total != taps*chunks*64");
+    const int64_t out_c = d->geglu ? d->n_total / 2 : d->n_total;
+    WIW_REQUIRE(d->out_dim[0] == out_c, "out channel extent must equal n_total (n_total/2 for geglu)");
+    WIW_REQUIRE(!d->tab || (d->tab_div > 0 && d->tab_mod > 0), "tab needs tab_div, tab_mod > 0");
+    WIW_REQUIRE(!d->tab || !d->geglu, "tab with geglu is not supported");
+
+    GemmArgs g;
+    memset(&g, 0, sizeof(g));
+    g.bx = d->bx; g.by = d->by;
+    g.dim_x = (int)d->out_dim[1]; g.dim_y = (int)d->out_dim[2];
+    g.tiles_x = (g.dim_x + g.bx - 1) / g.bx;
+    g.tiles_y = (g.dim_y + g.by - 1) / g.by;
+    g.n_tiles = (int)(d->n_total / d->bn);
+    const long long m_tiles = (long long)g.tiles_x * g.tiles_y * d->out_dim[3];
+    WIW_REQUIRE(m_tiles * g.n_tiles < (1LL << 31), "too many tiles");
+    g.total_tiles = (int)(m_tiles * g.n_tiles);
+    g.bn = d->bn;
+    g.num_taps = d->num_taps; g.chunks_per_tap = d->chunks_per_tap;
+    g.geglu = d->geglu ? 1 : 0;
+    g.out_cols_per_tile = g.geglu ? d->bn / 2 : d->bn;
+    g.has_res = d->res ? 1 : 0; g.has_aux = d->aux ? 1 : 0;
+    g.tab_div = d->tab_div; g.tab_mod = d->tab_mod; g.n_total = (int)d->n_total;
+    g.bias = d->bias; g.tab = d->tab;
+    g.s_acc = d->s_acc; g.s_res = d->s_res; g.s_aux = d->s_aux;
+    for (int i = 0; i < d->num_taps; ++i) {
+        g.tap_cbase[i] = d->tap_cbase[i]; g.tap_ox[i] = d->tap_ox[i]; g.tap_p[i] = d->tap_p[i]; g.tap_oy[i] = d->tap_oy[i];
+    }
+    int cols = 2 * ((g.bn <= 32) ? 32 : (g.bn <= 64 ? 64 : (g.bn <= 128 ? 128 : 256)));
+    g.tmem_cols = cols;       // power of two in [64, 512]
+
+    const int stage_bytes = kBlockM * kBlockK * 2 + g.bn * kBlockK * 2;
+    const int fixed = 1024 /*align slack*/ + kOutBufs * kEpiChunkBytes + (g.has_res ? kResSlots * kEpiChunkBytes : 0) +
+                      (g.has_aux ? kResSlots * kEpiChunkBytes : 0) + 256 /*barriers*/;
+    int stages = (kSmemBudget - fixed) / stage_bytes;
+    if (stages > kMaxStages) stages = kMaxStages;
+    WIW_REQUIRE(stages >= 2, "not enough shared memory for 2 pipeline stages");
+    g.stages = stages;
+    const int smem_bytes = fixed + stages * stage_bytes;
+
+    // ---- tensor maps
+    CUtensorMap tm_a, tm_b, tm_out, tm_res, tm_aux;
+    {
+        uint64_t dims[5], strides[4];
+        uint32_t box[5] = {(uint32_t)kBlockK, (uint32_t)d->bx, 1u, (uint32_t)d->by, 1u};
+        for (int i = 0; i < 5; ++i) dims[i] = (uint64_t)d->a_dim[i];
+        for (int i = 1; i < 5; ++i) strides[i - 1] = (uint64_t)d->a_stride[i] * 2;
+        if (encode_tmap(&tm_a, d->a, 5, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return 3;
+    }
+    {
+        uint64_t dims[2] = {(uint64_t)d->k_total, (uint64_t)d->n_total};
+        uint64_t strides[1] = {(uint64_t)d->k_total * 2};
+        uint32_t box[2] = {(uint32_t)kBlockK, (uint32_t)d->bn};
+        if (encode_tmap(&tm_b, d->w, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return 3;
+    }
+    auto enc_out = [&](CUtensorMap* m, const void* p, const int64_t* st) -> int {
+        uint64_t dims[4], strides[3];
+        uint32_t box[4] = {(uint32_t)kEpiCols, (uint32_t)d->bx, (uint32_t)d->by, 1u};
+        for (int i = 0; i < 4; ++i) dims[i] = (uint64_t)d->out_dim[i];
+        for (int i = 1; i < 4; ++i) strides[i - 1] = (uint64_t)st[i] * 2;
+        return encode_tmap(m, p, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B);
+    };
+    if (enc_out(&tm_out, d->out, d->out_stride)) return 3;
+    if (d->res) { if (enc_out(&tm_res, d->res, d->res_stride)) return 3; } else tm_res = tm_out;
+    if (d->aux) { if (enc_out(&tm_aux, d->aux, d->aux_stride)) return 3; } else tm_aux = tm_out;
+
+    static bool attr_set = false;
+    if (!attr_set) {
+        WIW_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+        attr_set = true;
+    }
+    int grid = num_sms();
+    if (grid > g.total_tiles) grid = g.total_tiles;
+    conv_gemm_kernel<<<grid, kThreads, smem_bytes, stream>>>(tm_a, tm_b, tm_out, tm_res, tm_aux, g);
+    WIW_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace wiw
+
+extern "C" int wiw_conv_gemm(const wiw_gemm_desc* d, wiw_stream_t stream) {
+    return wiw::launch_conv_gemm(d, static_cast<cudaStream_t>(stream));
+}

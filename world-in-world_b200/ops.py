@@ -1,0 +1,196 @@
+"""Host-side op wrappers: build the C-ABI descriptors for the sm_100a kernels.
+
+Activations are fp16 channels-last torch CUDA tensors; every function launches on the
+current torch stream and returns immediately.  No op here has a torch fallback.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from . import lib as L
+
+
+# ----------------------------------------------------------------------------- weights
+@dataclass
+class GemmWeight:
+    """fp16 [n, k] K-major weight (+ fp32 bias) ready for wiw_conv_gemm."""
+    w: torch.Tensor
+    bias: Optional[torch.Tensor]
+    n: int
+    k: int
+    cin: int                 # channels per tap (multiple of 64, after padding)
+    taps: int
+    geglu: bool = False
+    bn: int = 0
+    n_real: int = 0          # un-padded output channels
+
+
+def pick_bn(n: int, geglu: bool = False) -> int:
+    step = 64 if geglu else 32
+    for bn in range(256, 0, -step):
+        if n % bn == 0:
+            return bn
+    raise ValueError(f"N={n} is not a multiple of {step}")
+
+
+def _pad_to(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
+def prep_linear(weight: torch.Tensor, bias: Optional[torch.Tensor], device, geglu: bool = False) -> GemmWeight:
+    """nn.Linear weight [n, k] -> K-major fp16.  For GEGLU (`net.0.proj`, [8C, C]: first half value,
+    second half gate -- activations.py:120) rows are interleaved per N-tile as [bn/2 value | bn/2 gate]."""
+    n, k = weight.shape
+    kp, npad = _pad_to(k, 64), _pad_to(n, 64 if geglu else 32)
+    w = torch.zeros(npad, kp, dtype=torch.float32)
+    w[:n, :k] = weight.float()
+    b = torch.zeros(npad, dtype=torch.float32)
+    if bias is not None:
+        b[:n] = bias.float()
+    bn = pick_bn(npad, geglu)
+    if geglu:
+        assert npad == n and n % 2 == 0
+        half, hb = n // 2, bn // 2
+        idx = []
+        for t in range(n // bn):
+            idx += list(range(t * hb, (t + 1) * hb)) + list(range(half + t * hb, half + (t + 1) * hb))
+        idx = torch.tensor(idx)
+        w, b = w[idx], b[idx]
+    return GemmWeight(w=w.to(device=device, dtype=torch.float16).contiguous(),
+                      bias=(b.to(device) if bias is not None else None), n=npad, k=kp, cin=kp, taps=1,
+                      geglu=geglu, bn=bn, n_real=n)
+
+
+def prep_conv(weight: torch.Tensor, bias: Optional[torch.Tensor], device) -> GemmWeight:
+    """Conv2d [cout, cin, 3, 3] / [cout, cin, 1, 1] or Conv3d [cout, cin, 3, 1, 1] -> [cout, taps*cin_p]
+    with tap-major, channel-minor K (tap index = ky*3 + kx, or kt)."""
+    cout, cin = weight.shape[:2]
+    taps = int(torch.tensor(weight.shape[2:]).prod())
+    cp, npad = _pad_to(cin, 64), _pad_to(cout, 32)
+    w = torch.zeros(npad, taps, cp, dtype=torch.float32)
+    w[:cout, :, :cin] = weight.float().reshape(cout, cin, taps).permute(0, 2, 1)
+    b = torch.zeros(npad, dtype=torch.float32)
+    if bias is not None:
+        b[:cout] = bias.float()
+    return GemmWeight(w=w.reshape(npad, taps * cp).to(device=device, dtype=torch.float16).contiguous(),
+                      bias=b.to(device), n=npad, k=taps * cp, cin=cp, taps=taps, bn=pick_bn(npad), n_real=cout)
+
+
+# ----------------------------------------------------------------------------- GEMM launches
+def _box(width: int) -> Tuple[int, int]:
+    """M-tile = by rows of bx pixels (bx*by = 128); bx = largest power of two <= min(width, 128)."""
+    bx = 1
+    while bx * 2 <= min(width, 128):
+        bx *= 2
+    return bx, 128 // bx
+
+
+def _launch(a: torch.Tensor, a_dim, a_stride, gw: GemmWeight, out: torch.Tensor, out_dim, out_stride,
+            taps: Sequence[Tuple[int, int, int, int]], bx: int, by: int,
+            res: Optional[torch.Tensor], aux: Optional[torch.Tensor], tab: Optional[torch.Tensor],
+            tab_div: int, tab_mod: int, s_acc: float, s_res: float, s_aux: float, use_bias: bool = True) -> None:
+    lib = L.require_device()
+    d = L.GemmDesc()
+    d.a = a.data_ptr()
+    for i in range(5):
+        d.a_dim[i] = int(a_dim[i]); d.a_stride[i] = int(a_stride[i])
+    d.w = gw.w.data_ptr(); d.k_total = gw.k; d.n_total = gw.n
+    d.out = out.data_ptr()
+    for i in range(4):
+        d.out_dim[i] = int(out_dim[i]); d.out_stride[i] = int(out_stride[i])
+        d.res_stride[i] = int(out_stride[i]); d.aux_stride[i] = int(out_stride[i])
+    d.res = res.data_ptr() if res is not None else None
+    d.aux = aux.data_ptr() if aux is not None else None
+    d.bias = gw.bias.data_ptr() if (gw.bias is not None and use_bias) else None
+    d.tab = tab.data_ptr() if tab is not None else None
+    d.tab_div, d.tab_mod = int(tab_div), int(tab_mod)
+    d.s_acc, d.s_res, d.s_aux = float(s_acc), float(s_res), float(s_aux)
+    d.bx, d.by, d.bn, d.geglu = bx, by, gw.bn, int(gw.geglu)
+    d.num_taps, d.chunks_per_tap = len(taps), gw.cin // 64
+    for i, (cb, ox, p, oy) in enumerate(taps):
+        d.tap_cbase[i], d.tap_ox[i], d.tap_p[i], d.tap_oy[i] = cb, ox, p, oy
+    L.check(lib.wiw_conv_gemm(d, L.stream_ptr()))
+
+
+def _chk(x: torch.Tensor) -> None:
+    if x.dtype != torch.float16 or not x.is_cuda or not x.is_contiguous():
+        raise L.WiwError(f"expected a contiguous fp16 CUDA tensor, got {x.dtype} {x.device} contiguous={x.is_contiguous()}")
+
+
+def linear(x: torch.Tensor, gw: GemmWeight, res=None, aux=None, tab=None, tab_div=1, tab_mod=1,
+           s_acc=1.0, s_res=1.0, s_aux=1.0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """y[M, n] = epilogue(x[M, k] @ W^T): nn.Linear (+ fused bias / residual / GEGLU / row-group table)."""
+    _chk(x)
+    m, k = x.shape
+    assert k == gw.k, (k, gw.k)
+    n_out = gw.n // 2 if gw.geglu else gw.n
+    if out is None:
+        out = torch.empty(m, n_out, dtype=torch.float16, device=x.device)
+    _launch(x, (k, m, 1, 1, 1), (1, k, m * k, m * k, m * k), gw, out, (n_out, m, 1, 1), (1, n_out, m * n_out, m * n_out),
+            [(0, 0, 0, 0)], 128, 1, res, aux, tab, tab_div, tab_mod, s_acc, s_res, s_aux)
+    return out
+
+
+def conv3x3(x: torch.Tensor, gw: GemmWeight, res=None, tab=None, tab_div=1, tab_mod=1,
+            s_acc=1.0, s_res=1.0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Conv2d 3x3 stride 1 pad 1 on channels-last x[N, H, W, C] (C % 64 == 0)."""
+    _chk(x)
+    n, h, w, c = x.shape
+    assert c == gw.cin and gw.taps == 9
+    if out is None:
+        out = torch.empty(n, h, w, gw.n, dtype=torch.float16, device=x.device)
+    bx, by = _box(w)
+    taps = [(0, kx - 1, 0, ky - 1) for ky in range(3) for kx in range(3)]
+    _launch(x, (c, w, 1, h, n), (1, c, w * c, w * c, h * w * c), gw, out, (gw.n, w, h, n), (1, gw.n, w * gw.n, h * w * gw.n),
+            taps, bx, by, res, None, tab, tab_div, tab_mod, s_acc, s_res, 1.0)
+    return out
+
+
+def conv1x1(x: torch.Tensor, gw: GemmWeight, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Conv2d 1x1 (conv_shortcut, resnet.py:311) == linear over pixels."""
+    n, h, w, c = x.shape
+    y = linear(x.view(n * h * w, c), gw, out=None if out is None else out.view(n * h * w, gw.n))
+    return y.view(n, h, w, gw.n)
+
+
+def conv3x3_s2(x: torch.Tensor, gw: GemmWeight, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Conv2d 3x3 stride 2 pad 1 (Downsample2D, downsampling.py:69-146) through a space-to-depth view:
+    input pixel (2Y+py, 2X+px) -> coords (c + px*C, X, py, Y, n); tap d=-1 reads parity 1 at X-1 / Y-1."""
+    _chk(x)
+    n, h, w, c = x.shape
+    assert c == gw.cin and gw.taps == 9 and h % 2 == 0 and w % 2 == 0
+    ho, wo = h // 2, w // 2
+    if out is None:
+        out = torch.empty(n, ho, wo, gw.n, dtype=torch.float16, device=x.device)
+    bx, by = _box(wo)
+
+    def par(d):           # filter offset d-1 in {-1,0,1} -> (parity, coarse offset)
+        return [(1, -1), (0, 0), (1, 0)][d]
+
+    taps = []
+    for ky in range(3):
+        py, oy = par(ky)
+        for kx in range(3):
+            px, ox = par(kx)
+            taps.append((px * c, ox, py, oy))
+    _launch(x, (2 * c, wo, 2, ho, n), (1, 2 * c, w * c, 2 * w * c, h * w * c), gw, out,
+            (gw.n, wo, ho, n), (1, gw.n, wo * gw.n, ho * wo * gw.n), taps, bx, by,
+            None, None, None, 1, 1, 1.0, 1.0, 1.0)
+    return out
+
+
+def tconv3(x: torch.Tensor, gw: GemmWeight, res=None, tab=None, tab_div=1, tab_mod=1,
+           s_acc=1.0, s_res=1.0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Conv3d (3,1,1) pad (1,0,0) along frames on x[B, F, S, C] (TemporalResnetBlock, resnet.py:570,586)."""
+    _chk(x)
+    b, f, s, c = x.shape
+    assert c == gw.cin and gw.taps == 3
+    if out is None:
+        out = torch.empty(b, f, s, gw.n, dtype=torch.float16, device=x.device)
+    taps = [(0, 0, 0, kt - 1) for kt in range(3)]
+    _launch(x, (c, s, 1, f, b), (1, c, s * c, s * c, f * s * c), gw, out, (gw.n, s, f, b), (1, gw.n, s * gw.n, f * s * gw.n),
+            taps, 128, 1, res, None, tab, tab_div, tab_mod, s_acc, s_res, 1.0)
+    return out
