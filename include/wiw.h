@@ -38,7 +38,7 @@ int wiw_device_ok(void);
  * Implicit-GEMM contraction on tcgen05 tensor cores (TMA-fed, TMEM accumulators).
  *
  *   out[n, y, x, :] = s_acc * ( sum_taps sum_c A[c + cbase_t, x + ox_t, p_t, y + oy_t, n] * W[:, t*Cin + c]
- *                               + bias[:] + tab[((n*Y + y)*X + x) / tab_div % tab_mod, :] )
+ *                               + bias[:] + tab[((n*Y + y)*X + x) / tab_div % tab_mod, :] )      (act applied here)
  *                     + s_res * res[n, y, x, :] + s_aux * aux[n, y, x, :]
  *
  * A is a 5-D strided view (c, x, p, y, n) of an fp16 tensor (c contiguous); out-of-range
@@ -67,7 +67,7 @@ typedef struct {
     const void* aux;        /* optional fp16, same extents as out */
     int64_t aux_stride[4];
     const float* bias;      /* optional fp32 [n_total] */
-    const float* tab;       /* optional fp32 [tab_rows][n_total] */
+    const void* tab;        /* optional fp16 [tab_rows][tab_stride] */
     int32_t tab_div;
     int32_t tab_mod;
     float s_acc, s_res, s_aux;
@@ -80,6 +80,8 @@ typedef struct {
     int32_t tap_ox[9];
     int32_t tap_p[9];
     int32_t tap_oy[9];
+    int32_t tab_stride;     /* row stride of tab in elements (0 = n_total) */
+    int32_t act;            /* 0 none, 1 SiLU applied to (acc + bias + tab) */
 } wiw_gemm_desc;
 
 int wiw_conv_gemm(const wiw_gemm_desc* d, wiw_stream_t stream);
@@ -99,7 +101,7 @@ int wiw_groupnorm_workspace_floats(int samples, int groups);
 int wiw_groupnorm(const void* x, void* y, int samples, long long rows_per_sample, int C, int G,
                   const float* gamma, const float* beta, float eps, int silu, float* workspace, wiw_stream_t stream);
 int wiw_layernorm(const void* x, void* y, long long M, int C, const float* gamma, const float* beta, float eps,
-                  const float* tab, int tab_div, int tab_mod, wiw_stream_t stream);
+                  const void* tab /* fp16 [tab_mod][C] */, int tab_div, int tab_mod, wiw_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * EDM / Euler sampler glue (bit-exact fp32 arithmetic, no FMA contraction).
@@ -124,6 +126,10 @@ int wiw_upsample_nearest2x(const void* x, void* y, int N, int H, int W, int C, w
 /* Temporal self-attention over F frames per (batch element, pixel, head), head_dim 64
  * (attention.py:736): qkv fp16 [B][F][S][3C] -> out [B][F][S][C]. */
 int wiw_attention_temporal(const void* qkv, void* out, int B, int F, int S, int C, wiw_stream_t stream);
+/* Spatial self-attention softmax(q k^T / 8) v per (image, head), head_dim 64, tcgen05 flash kernel
+ * (F.scaled_dot_product_attention at attention_processor.py:2383 <- attention.py:507):
+ * qkv fp16 [images][S][3C] (q | k | v, head h at columns h*64), out fp16 [images][S][C]. */
+int wiw_attention_spatial(const void* qkv, void* out, int images, int S, int C, wiw_stream_t stream);
 /* In-place softmax(scale * row) on fp16 [rows][S] (VAE mid-block attention, unet_3d_blocks.py:958-969). */
 int wiw_softmax_rows(void* s, long long rows, int S, float scale, wiw_stream_t stream);
 /* Batched transpose fp16 [batch][R][C] -> [batch][C][R]. */

@@ -58,11 +58,11 @@ def test_linear_full_epilogue():
     x = rnd(m, k, seed=1).half().to(DEV)
     w, b = rnd(n, k, seed=2, scale=k ** -0.5), rnd(n, seed=3)
     res, aux = rnd(m, n, seed=4).half().to(DEV), rnd(m, n, seed=5).half().to(DEV)
-    tab = rnd(5, n, seed=6).to(DEV)
+    tab = rnd(5, n, seed=6).half().to(DEV)
     gw = ops.prep_linear(w, b, DEV)
     y = ops.linear(x, gw, res=res, aux=aux, tab=tab, tab_div=50, tab_mod=5, s_acc=0.4, s_res=0.4, s_aux=0.6)
     rows = (torch.arange(m, device=DEV) // 50) % 5
-    ref = 0.4 * (F.linear(x.float(), w.half().float().to(DEV), b.to(DEV)) + tab[rows]) + 0.4 * res.float() + 0.6 * aux.float()
+    ref = 0.4 * (F.linear(x.float(), w.half().float().to(DEV), b.to(DEV)) + tab.float()[rows]) + 0.4 * res.float() + 0.6 * aux.float()
     close(y, ref, "linear epilogue")
 
 
@@ -83,11 +83,11 @@ def test_conv3x3(n, h, w, cin, cout):
     x = rnd(n, h, w, cin, seed=1).half().to(DEV)
     wt, b = rnd(cout, cin, 3, 3, seed=2, scale=(9 * cin) ** -0.5), rnd(cout, seed=3)
     gw = ops.prep_conv(wt, b, DEV)
-    tab = rnd(n, gw.n, seed=4).to(DEV)
+    tab = rnd(n, gw.n, seed=4).half().to(DEV)
     res = rnd(n, h, w, gw.n, seed=5).half().to(DEV)
     y = ops.conv3x3(x, gw, res=res, tab=tab, tab_div=h * w, tab_mod=n)
     ref = F.conv2d(x.float().permute(0, 3, 1, 2), wt.half().float().to(DEV), b.to(DEV), padding=1).permute(0, 2, 3, 1)
-    ref = ref + tab[:, None, None, :cout] + res.float()[..., :cout]
+    ref = ref + tab.float()[:, None, None, :cout] + res.float()[..., :cout]
     close(y[..., :cout], ref, f"conv3x3 {n}x{h}x{w}x{cin}->{cout}")
 
 
@@ -120,11 +120,11 @@ def test_tconv3(b_, f, s, c):
     wt, b = rnd(c, c, 3, 1, 1, seed=2, scale=(3 * c) ** -0.5), rnd(c, seed=3)
     gw = ops.prep_conv(wt, b, DEV)
     res = rnd(b_, f, s, c, seed=4).half().to(DEV)
-    tab = rnd(b_ * f, c, seed=5).to(DEV)
+    tab = rnd(b_ * f, c, seed=5).half().to(DEV)
     y = ops.tconv3(x, gw, res=res, tab=tab, tab_div=s, tab_mod=b_ * f, s_acc=0.3, s_res=1.0)
     xr = x.float().permute(0, 3, 1, 2).unsqueeze(-1)                     # [B, C, F, S, 1]
     ref = F.conv3d(xr, wt.half().float().to(DEV), b.to(DEV), padding=(1, 0, 0)).squeeze(-1).permute(0, 2, 3, 1)
-    ref = 0.3 * (ref + tab.view(b_, f, 1, c)) + res.float()
+    ref = 0.3 * (ref + tab.float().view(b_, f, 1, c)) + res.float()
     close(y, ref, "tconv3")
 
 

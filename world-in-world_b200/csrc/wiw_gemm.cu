@@ -33,8 +33,9 @@ struct GemmArgs {
     int bn, stages, num_taps, chunks_per_tap;
     int out_cols_per_tile, geglu, has_res, has_aux;
     int tab_div, tab_mod, n_total, tmem_cols;
+    int tab_stride, act;
     const float* bias;
-    const float* tab;
+    const __half* tab;
     float s_acc, s_res, s_aux;
     int tap_cbase[9], tap_ox[9], tap_p[9], tap_oy[9];
 };
@@ -205,13 +206,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             const TileCoord t = decode_tile(g, tile);
             const int acc_n0 = t.n_tile * g.bn;                       // first GEMM column of this tile
             const int out_c0 = t.n_tile * g.out_cols_per_tile;        // first output channel
-            const float* tab_row = nullptr;
+            const __half* tab_row = nullptr;
             if (g.tab != nullptr) {
                 const int x = t.x0 + (row % g.bx), y = t.y0 + (row / g.bx);
                 long long grow = ((long long)t.img * g.dim_y + y) * g.dim_x + x;
                 if (grow < 0) grow = 0;
                 int gi = int((grow / g.tab_div) % g.tab_mod);
-                tab_row = g.tab + (size_t)gi * g.n_total;
+                tab_row = g.tab + (size_t)gi * g.tab_stride;
             }
             mbar_wait(bar_tfull + 8 * as, aph);
             tc_fence_after();
@@ -234,10 +235,19 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                     }
                     if (tab_row != nullptr) {
 #pragma unroll
-                        for (int c = 0; c < kEpiCols; c += 4) {
-                            const float4 b4 = __ldg(reinterpret_cast<const float4*>(tab_row + nb + c));
-                            v[c] += b4.x; v[c + 1] += b4.y; v[c + 2] += b4.z; v[c + 3] += b4.w;
+                        for (int c = 0; c < kEpiCols; c += 8) {
+                            const uint4 u = __ldg(reinterpret_cast<const uint4*>(tab_row + nb + c));
+                            const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const float2 f = __half22float2(h[e]);
+                                v[c + 2 * e] += f.x; v[c + 2 * e + 1] += f.y;
+                            }
                         }
+                    }
+                    if (g.act == 1) {
+#pragma unroll
+                        for (int c = 0; c < kEpiCols; ++c) v[c] = silu_f(v[c]);
                     }
                 }
                 if (g.geglu) {
@@ -349,6 +359,9 @@ static int launch_conv_gemm(const wiw_gemm_desc* d, cudaStream_t stream) {
     WIW_REQUIRE(d->out_dim[0] == out_c, "out channel extent must equal n_total (n_total/2 for geglu)");
     WIW_REQUIRE(!d->tab || (d->tab_div > 0 && d->tab_mod > 0), "tab needs tab_div, tab_mod > 0");
     WIW_REQUIRE(!d->tab || !d->geglu, "tab with geglu is not supported");
+    WIW_REQUIRE(!d->tab || (d->tab_stride % 8 == 0), "tab_stride must be a multiple of 8");
+    WIW_REQUIRE(d->act == 0 || d->act == 1, "act must be 0 (none) or 1 (SiLU)");
+    WIW_REQUIRE(!(d->act && d->geglu), "act with geglu is not supported");
 
     GemmArgs g;
     memset(&g, 0, sizeof(g));
@@ -366,7 +379,8 @@ static int launch_conv_gemm(const wiw_gemm_desc* d, cudaStream_t stream) {
     g.out_cols_per_tile = g.geglu ? d->bn / 2 : d->bn;
     g.has_res = d->res ? 1 : 0; g.has_aux = d->aux ? 1 : 0;
     g.tab_div = d->tab_div; g.tab_mod = d->tab_mod; g.n_total = (int)d->n_total;
-    g.bias = d->bias; g.tab = d->tab;
+    g.tab_stride = d->tab_stride > 0 ? d->tab_stride : (int)d->n_total; g.act = d->act;
+    g.bias = d->bias; g.tab = static_cast<const __half*>(d->tab);
     g.s_acc = d->s_acc; g.s_res = d->s_res; g.s_aux = d->s_aux;
     for (int i = 0; i < d->num_taps; ++i) {
         g.tap_cbase[i] = d->tap_cbase[i]; g.tap_ox[i] = d->tap_ox[i]; g.tap_p[i] = d->tap_p[i]; g.tap_oy[i] = d->tap_oy[i];

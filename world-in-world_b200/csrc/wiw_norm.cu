@@ -118,14 +118,14 @@ __global__ void gn_apply_kernel(const __half* __restrict__ x, __half* __restrict
 // y = LN(x + tab[(row / tab_div) % tab_mod]) * gamma + beta; optionally also writes nothing else.
 template <int VPL>     // 16-byte vectors per lane (C <= 256*VPL)
 __global__ void layernorm_kernel(const __half* __restrict__ x, __half* __restrict__ y, const float* __restrict__ gamma,
-                                 const float* __restrict__ beta, const float* __restrict__ tab, int tab_div, int tab_mod,
+                                 const float* __restrict__ beta, const __half* __restrict__ tab, int tab_div, int tab_mod,
                                  long long M, int C, float eps) {
     const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= M) return;
     const int lane = threadIdx.x & 31;
     const int nvec = C >> 3;
     float v[VPL][8];
-    const float* trow = tab ? tab + (size_t)((row / tab_div) % tab_mod) * C : nullptr;
+    const __half* trow = tab ? tab + (size_t)((row / tab_div) % tab_mod) * C : nullptr;
     float sum = 0.f;
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
@@ -142,7 +142,7 @@ __global__ void layernorm_kernel(const __half* __restrict__ x, __half* __restric
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
                     // the reference adds in fp16 (hidden_states + emb, transformer_temporal.py:360)
-                    v[i][e] = __half2float(__float2half_rn(v[i][e] + trow[vi * 8 + e]));
+                    v[i][e] = __half2float(__float2half_rn(v[i][e] + __half2float(trow[vi * 8 + e])));
                 }
             }
 #pragma unroll
@@ -230,7 +230,8 @@ extern "C" int wiw_groupnorm(const void* x, void* y, int samples, long long rows
 }
 
 extern "C" int wiw_layernorm(const void* x, void* y, long long M, int C, const float* gamma, const float* beta,
-                             float eps, const float* tab, int tab_div, int tab_mod, wiw_stream_t stream_) {
+                             float eps, const void* tab_, int tab_div, int tab_mod, wiw_stream_t stream_) {
+    const __half* tab = static_cast<const __half*>(tab_);
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     WIW_REQUIRE(x && y && gamma && beta, "null pointer");
     WIW_REQUIRE(C % 8 == 0 && C <= 2048, "LayerNorm supports C % 8 == 0, C <= 2048");

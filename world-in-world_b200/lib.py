@@ -35,6 +35,7 @@ class GemmDesc(ctypes.Structure):
         ("num_taps", ctypes.c_int32), ("chunks_per_tap", ctypes.c_int32),
         ("tap_cbase", ctypes.c_int32 * 9), ("tap_ox", ctypes.c_int32 * 9),
         ("tap_p", ctypes.c_int32 * 9), ("tap_oy", ctypes.c_int32 * 9),
+        ("tab_stride", ctypes.c_int32), ("act", ctypes.c_int32),
     ]
 
 
@@ -56,6 +57,7 @@ SYMBOLS = {
     "wiw_concat_channels": (_I, [_VP, _VP, _VP, _LL, _I, _I, _VP]),
     "wiw_upsample_nearest2x": (_I, [_VP, _VP, _I, _I, _I, _I, _VP]),
     "wiw_attention_temporal": (_I, [_VP, _VP, _I, _I, _I, _I, _VP]),
+    "wiw_attention_spatial": (_I, [_VP, _VP, _I, _I, _I, _VP]),
     "wiw_softmax_rows": (_I, [_VP, _LL, _I, _F, _VP]),
     "wiw_transpose": (_I, [_VP, _VP, _I, _I, _I, _VP]),
     "wiw_frames_to_u8": (_I, [_VP, _VP, _LL, _LL, _I, _VP]),

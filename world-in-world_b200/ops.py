@@ -91,7 +91,8 @@ def _box(width: int) -> Tuple[int, int]:
 def _launch(a: torch.Tensor, a_dim, a_stride, gw: GemmWeight, out: torch.Tensor, out_dim, out_stride,
             taps: Sequence[Tuple[int, int, int, int]], bx: int, by: int,
             res: Optional[torch.Tensor], aux: Optional[torch.Tensor], tab: Optional[torch.Tensor],
-            tab_div: int, tab_mod: int, s_acc: float, s_res: float, s_aux: float, use_bias: bool = True) -> None:
+            tab_div: int, tab_mod: int, s_acc: float, s_res: float, s_aux: float, use_bias: bool = True,
+            act: int = 0) -> None:
     lib = L.require_device()
     d = L.GemmDesc()
     d.a = a.data_ptr()
@@ -107,6 +108,11 @@ def _launch(a: torch.Tensor, a_dim, a_stride, gw: GemmWeight, out: torch.Tensor,
     d.bias = gw.bias.data_ptr() if (gw.bias is not None and use_bias) else None
     d.tab = tab.data_ptr() if tab is not None else None
     d.tab_div, d.tab_mod = int(tab_div), int(tab_mod)
+    if tab is not None:
+        if tab.dtype != torch.float16 or tab.stride(-1) != 1:
+            raise L.WiwError("tab must be fp16 with contiguous columns")
+        d.tab_stride = int(tab.stride(0)) if tab.dim() == 2 else int(tab.shape[-1])
+    d.act = int(act)
     d.s_acc, d.s_res, d.s_aux = float(s_acc), float(s_res), float(s_aux)
     d.bx, d.by, d.bn, d.geglu = bx, by, gw.bn, int(gw.geglu)
     d.num_taps, d.chunks_per_tap = len(taps), gw.cin // 64
@@ -121,7 +127,7 @@ def _chk(x: torch.Tensor) -> None:
 
 
 def linear(x: torch.Tensor, gw: GemmWeight, res=None, aux=None, tab=None, tab_div=1, tab_mod=1,
-           s_acc=1.0, s_res=1.0, s_aux=1.0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+           s_acc=1.0, s_res=1.0, s_aux=1.0, out: Optional[torch.Tensor] = None, act: int = 0) -> torch.Tensor:
     """y[M, n] = epilogue(x[M, k] @ W^T): nn.Linear (+ fused bias / residual / GEGLU / row-group table)."""
     _chk(x)
     m, k = x.shape
@@ -130,7 +136,7 @@ def linear(x: torch.Tensor, gw: GemmWeight, res=None, aux=None, tab=None, tab_di
     if out is None:
         out = torch.empty(m, n_out, dtype=torch.float16, device=x.device)
     _launch(x, (k, m, 1, 1, 1), (1, k, m * k, m * k, m * k), gw, out, (n_out, m, 1, 1), (1, n_out, m * n_out, m * n_out),
-            [(0, 0, 0, 0)], 128, 1, res, aux, tab, tab_div, tab_mod, s_acc, s_res, s_aux)
+            [(0, 0, 0, 0)], 128, 1, res, aux, tab, tab_div, tab_mod, s_acc, s_res, s_aux, act=act)
     return out
 
 
@@ -193,4 +199,142 @@ def tconv3(x: torch.Tensor, gw: GemmWeight, res=None, tab=None, tab_div=1, tab_m
     taps = [(0, 0, 0, kt - 1) for kt in range(3)]
     _launch(x, (c, s, 1, f, b), (1, c, s * c, s * c, f * s * c), gw, out, (gw.n, s, f, b), (1, gw.n, s * gw.n, f * s * gw.n),
             taps, 128, 1, res, None, tab, tab_div, tab_mod, s_acc, s_res, 1.0)
+    return out
+
+
+# ----------------------------------------------------------------------------- norms
+@dataclass
+class NormWeight:
+    gamma: torch.Tensor      # fp32 [C]
+    beta: torch.Tensor       # fp32 [C]
+
+
+def prep_norm(weight: torch.Tensor, bias: torch.Tensor, device) -> NormWeight:
+    return NormWeight(weight.float().to(device).contiguous(), bias.float().to(device).contiguous())
+
+
+_gn_ws = {}
+
+
+def group_norm(x: torch.Tensor, nw: NormWeight, samples: int, eps: float, silu: bool, groups: int = 32,
+               out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """nn.GroupNorm(32)(+SiLU) over x viewed as [samples][rows][C] (channels-last)."""
+    _chk(x)
+    lib = L.require_device()
+    c = x.shape[-1]
+    rows = x.numel() // c // samples
+    if out is None:
+        out = torch.empty_like(x)
+    need = lib.wiw_groupnorm_workspace_floats(samples, groups)
+    key = (x.device.index, torch.cuda.current_stream().cuda_stream)
+    ws = _gn_ws.get(key)
+    if ws is None or ws.numel() < need:
+        ws = torch.empty(max(need, 1 << 16), dtype=torch.float32, device=x.device)
+        _gn_ws[key] = ws
+    L.check(lib.wiw_groupnorm(x.data_ptr(), out.data_ptr(), samples, rows, c, groups, nw.gamma.data_ptr(),
+                              nw.beta.data_ptr(), float(eps), int(silu), ws.data_ptr(), L.stream_ptr()))
+    return out
+
+
+def layer_norm(x: torch.Tensor, nw: NormWeight, eps: float = 1e-5, tab: Optional[torch.Tensor] = None,
+               tab_div: int = 1, tab_mod: int = 1, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """nn.LayerNorm over the last axis of x[M, C]; optional fp16 pre-add of tab[(row // tab_div) % tab_mod]."""
+    _chk(x)
+    lib = L.require_device()
+    m, c = x.shape
+    if out is None:
+        out = torch.empty_like(x)
+    L.check(lib.wiw_layernorm(x.data_ptr(), out.data_ptr(), m, c, nw.gamma.data_ptr(), nw.beta.data_ptr(), float(eps),
+                              tab.data_ptr() if tab is not None else None, tab_div, tab_mod, L.stream_ptr()))
+    return out
+
+
+# ----------------------------------------------------------------------------- attention
+def attention_spatial(qkv: torch.Tensor, images: int, s: int, c: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """qkv [images*S, 3C] -> [images*S, C]: softmax(q k^T / 8) v per (image, head)."""
+    _chk(qkv)
+    lib = L.require_device()
+    assert qkv.shape == (images * s, 3 * c)
+    if out is None:
+        out = torch.empty(images * s, c, dtype=torch.float16, device=qkv.device)
+    L.check(lib.wiw_attention_spatial(qkv.data_ptr(), out.data_ptr(), images, s, c, L.stream_ptr()))
+    return out
+
+
+def attention_temporal(qkv: torch.Tensor, b: int, f: int, s: int, c: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """qkv [B*F*S, 3C] (rows ordered b, f, s) -> [B*F*S, C]: attention over the F frames of each pixel."""
+    _chk(qkv)
+    lib = L.require_device()
+    assert qkv.shape == (b * f * s, 3 * c)
+    if out is None:
+        out = torch.empty(b * f * s, c, dtype=torch.float16, device=qkv.device)
+    L.check(lib.wiw_attention_temporal(qkv.data_ptr(), out.data_ptr(), b, f, s, c, L.stream_ptr()))
+    return out
+
+
+# ----------------------------------------------------------------------------- small glue
+def concat_channels(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    _chk(a); _chk(b)
+    lib = L.require_device()
+    c1, c2 = a.shape[-1], b.shape[-1]
+    m = a.numel() // c1
+    out = torch.empty(*a.shape[:-1], c1 + c2, dtype=torch.float16, device=a.device)
+    L.check(lib.wiw_concat_channels(a.data_ptr(), b.data_ptr(), out.data_ptr(), m, c1, c2, L.stream_ptr()))
+    return out
+
+
+def upsample_nearest2x(x: torch.Tensor) -> torch.Tensor:
+    _chk(x)
+    lib = L.require_device()
+    n, h, w, c = x.shape
+    out = torch.empty(n, 2 * h, 2 * w, c, dtype=torch.float16, device=x.device)
+    L.check(lib.wiw_upsample_nearest2x(x.data_ptr(), out.data_ptr(), n, h, w, c, L.stream_ptr()))
+    return out
+
+
+def emb_silu(te: torch.Tensor, act: torch.Tensor, noise: torch.Tensor) -> torch.Tensor:
+    lib = L.require_device()
+    r, c = act.shape
+    out = torch.empty(r, c, dtype=torch.float16, device=act.device)
+    L.check(lib.wiw_emb_silu(te.data_ptr(), act.data_ptr(), noise.data_ptr(), out.data_ptr(), r, c, L.stream_ptr()))
+    return out
+
+
+def softmax_rows_(s: torch.Tensor, scale: float) -> torch.Tensor:
+    _chk(s)
+    lib = L.require_device()
+    rows, n = s.shape
+    L.check(lib.wiw_softmax_rows(s.data_ptr(), rows, n, float(scale), L.stream_ptr()))
+    return s
+
+
+def transpose(x: torch.Tensor) -> torch.Tensor:
+    """[batch, R, C] -> [batch, C, R]"""
+    _chk(x)
+    lib = L.require_device()
+    b, r, c = x.shape
+    out = torch.empty(b, c, r, dtype=torch.float16, device=x.device)
+    L.check(lib.wiw_transpose(x.data_ptr(), out.data_ptr(), b, r, c, L.stream_ptr()))
+    return out
+
+
+def nchw_to_nhwc(x: torch.Tensor, cs: int) -> torch.Tensor:
+    """fp16 [N, C, *spatial] -> channels-last [N, *spatial, cs] (zero-padded channels)."""
+    _chk(x)
+    lib = L.require_device()
+    n, c = x.shape[:2]
+    p = x.numel() // (n * c)
+    out = torch.empty(n, *x.shape[2:], cs, dtype=torch.float16, device=x.device)
+    L.check(lib.wiw_nchw_to_nhwc(x.data_ptr(), out.data_ptr(), n, c, p, cs, L.stream_ptr()))
+    return out
+
+
+def nhwc_to_nchw(x: torch.Tensor, c: int) -> torch.Tensor:
+    """channels-last fp16 [N, *spatial, cs] -> [N, c, *spatial] (first c channels)."""
+    _chk(x)
+    lib = L.require_device()
+    n, cs = x.shape[0], x.shape[-1]
+    p = x.numel() // (n * cs)
+    out = torch.empty(n, c, *x.shape[1:-1], dtype=torch.float16, device=x.device)
+    L.check(lib.wiw_nhwc_to_nchw(x.data_ptr(), out.data_ptr(), n, c, p, cs, L.stream_ptr()))
     return out
