@@ -13,6 +13,7 @@ Fixtures (all fp32 CPU, tiny geometry = wiw_b200.config.TINY_*):
   action_ids.npz     utils.svd_utils.action_ids_idx_encode on fixed action rows
   unet_tiny.npz      one UNet forward (inputs, output, a few block taps)
   vae_tiny.npz       one temporal-VAE decode
+  frontend_tiny.npz  VAE encode posterior mode + _resize_with_antialiasing (pipeline :231-252, :643-667)
   rollout_tiny.npz   the full vendored StableVideoDiffusionPipeline.__call__ (4 Euler steps,
                      CFG, injected latents): captured conditioning + final latents + frames
 """
@@ -78,6 +79,10 @@ def build_vae():
                                      latent_channels=c.latent_channels, down_block_types=("DownEncoderBlock2D",) * 4)
     sd = W.random_init(W.vae_decoder_param_spec(c), SEED_VAE)
     v.decoder.load_state_dict(sd, strict=True)
+    from wiw_b200.frontend import vae_encoder_param_spec
+    esd = W.random_init(vae_encoder_param_spec(c.block_out_channels, c.layers_per_block, c.latent_channels), SEED_VAE + 1)
+    missing, unexpected = v.load_state_dict(esd, strict=False)
+    assert not unexpected and all(k.startswith("decoder.") for k in missing), (missing[:3], unexpected[:3])
     return v.eval()
 
 
@@ -135,6 +140,16 @@ def main() -> None:
     dec = vae.decode(z, num_frames=F_).sample
     np.savez(os.path.join(OUT, "vae_tiny.npz"), z=z.numpy(), out=dec.numpy())
     print("vae_tiny out", tuple(dec.shape), float(dec.abs().mean()), float(dec.std()))
+
+    # ---- conditioning front-end: fp32 VAE encode (posterior mode) + antialiased CLIP resize --------
+    from diffusers.pipelines.stable_video_diffusion.pipeline_stable_video_diffusion import _resize_with_antialiasing
+    img_t = rng_normal(401, (1, 3, H_PX, W_PX)).clamp(-1, 1)
+    enc_mode = vae.encode(img_t).latent_dist.mode()
+    big = rng_normal(402, (1, 3, 288, 512)).clamp(-1, 1)
+    np.savez(os.path.join(OUT, "frontend_tiny.npz"), image=img_t.numpy(), latent_mode=enc_mode.numpy(),
+             resize_in=big.numpy().astype(np.float16), resize_out=_resize_with_antialiasing(big.half().float(), (224, 224)).numpy().astype(np.float16),
+             resize_up_out=_resize_with_antialiasing(img_t, (224, 224)).numpy().astype(np.float16))
+    print("frontend_tiny latent", tuple(enc_mode.shape), float(enc_mode.std()))
 
     # ---- full pipeline rollout ----------------------------------------------------------------
     from transformers import CLIPImageProcessor, CLIPVisionConfig, CLIPVisionModelWithProjection

@@ -1,0 +1,87 @@
+"""CPU-only checks of the host side: the C-ABI library loads and exports every symbol
+include/wiw.h declares, the product scheduler is bit-exact against the golden tables, the
+weight inventory matches the reference shapes, and the product refuses to run without a GPU."""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import wiw_b200  # noqa: F401
+from wiw_b200 import lib as L
+from wiw_b200 import weights as W
+from wiw_b200.config import FULL_UNET, FULL_VAE, TINY_UNET
+from wiw_b200.pipeline import sample_latent_noise_
+from wiw_b200.scheduler import EulerSchedule
+from oracle import svd_oracle as O
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    src = open(os.path.join(REPO, "include", "wiw.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(wiw_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    lib = L.load()
+    names = _declared_symbols()
+    assert len(names) >= 15
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/wiw.h but not exported"
+        assert n in L.SYMBOLS, f"{n} has no ctypes signature in wiw_b200/lib.py"
+    assert lib.wiw_abi_version() == L.ABI_VERSION
+    assert isinstance(lib.wiw_last_error(), bytes)
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
+def test_no_cpu_fallback():
+    with pytest.raises(L.WiwError):
+        L.require_device()
+    from wiw_b200 import ops
+    with pytest.raises(L.WiwError):
+        ops.layer_norm(torch.zeros(4, 64, dtype=torch.float16), ops.NormWeight(torch.ones(64), torch.zeros(64)))
+
+
+@pytest.mark.parametrize("n", [10, 25, 30])
+def test_product_scheduler_bit_exact(golden_dir, n):
+    g = np.load(os.path.join(golden_dir, "scheduler.npz"))
+    s = EulerSchedule(n)
+    assert s.sigmas.numpy().tobytes() == g[f"sigmas_{n}"].tobytes()
+    assert s.timesteps.numpy().tobytes() == g[f"timesteps_{n}"].tobytes()
+    assert np.float32(s.init_noise_sigma.item()).tobytes() == g[f"init_noise_sigma_{n}"].tobytes()
+    assert [s.index_for_timestep(t) for t in s.timesteps] == list(g[f"index_{n}"])
+    # the per-step scalars are the oracle's 0-dim tensor expressions
+    o = O.EulerSchedule(n)
+    for i, sc in enumerate(s.all_steps()):
+        sig = o.sigmas[i]
+        assert sc.div == float((sig ** 2 + 1) ** 0.5) and sc.c_out == float(-sig / (sig ** 2 + 1) ** 0.5)
+        assert sc.dt == float(o.sigmas[i + 1] - sig) and sc.sig2p1 == float(sig ** 2 + 1)
+
+
+def test_param_inventory():
+    spec = W.unet_param_spec(FULL_UNET)
+    assert sum(int(np.prod(s)) for _, s in spec) == 1_528_603_626
+    names = [n for n, _ in spec]
+    assert len(set(names)) == len(names)
+    assert "down_blocks.0.attentions.0.temporal_transformer_blocks.0.ff_in.net.0.proj.weight" in names
+    assert dict(spec)["add_action_proj.proj.weight"] == (256, 168)
+    vspec = W.vae_decoder_param_spec(FULL_VAE)
+    assert dict(vspec)["time_conv_out.weight"] == (3, 3, 3, 1, 1)
+    a = W.random_init(W.unet_param_spec(TINY_UNET)[:6], 3)
+    b = W.random_init(W.unet_param_spec(TINY_UNET)[:6], 3)
+    assert all(torch.equal(a[k], b[k]) for k in a)
+    with pytest.raises(KeyError):
+        W.check_state_dict({}, spec)
+
+
+def test_latent_noise_matches_oracle():
+    g = torch.Generator().manual_seed(0)
+    noise = torch.randn(8, 4, 2, 32, generator=g)
+    acts = torch.tensor([4, 2, 2, 1, 3, 3, 0, 2])
+    ref = O.sample_latent_noise(noise[None].clone(), acts[None])[0]
+    assert torch.equal(sample_latent_noise_(noise.clone(), acts), ref)
+    with pytest.raises(AssertionError):
+        sample_latent_noise_(torch.zeros(2, 4, 2, 8), torch.tensor([4, 2]))

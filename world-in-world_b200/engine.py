@@ -194,7 +194,7 @@ class UNetEngine(_Common):
                 ws.append(w_.float()); bs.append(b_.float())
         pad = (-off) % 256
         if pad:
-            ws.append(torch.zeros(pad, cfg.time_embed_dim)); bs.append(torch.zeros(pad))
+            ws.append(torch.zeros(pad, cfg.time_embed_dim, device=ws[0].device)); bs.append(torch.zeros(pad, device=ws[0].device))
         self.temb_all = ops.prep_linear(torch.cat(ws), torch.cat(bs), self.device)
         # frame-position embeddings are model constants: time_pos_embed(sincos(arange(F)))  (transformer_temporal.py:329-340)
         F = cfg.num_frames

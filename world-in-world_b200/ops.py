@@ -45,9 +45,10 @@ def prep_linear(weight: torch.Tensor, bias: Optional[torch.Tensor], device, gegl
     second half gate -- activations.py:120) rows are interleaved per N-tile as [bn/2 value | bn/2 gate]."""
     n, k = weight.shape
     kp, npad = _pad_to(k, 64), _pad_to(n, 64 if geglu else 32)
-    w = torch.zeros(npad, kp, dtype=torch.float32)
+    wd = weight.device                      # prepare where the checkpoint lives (GPU for the bench, CPU for tests)
+    w = torch.zeros(npad, kp, dtype=torch.float32, device=wd)
     w[:n, :k] = weight.float()
-    b = torch.zeros(npad, dtype=torch.float32)
+    b = torch.zeros(npad, dtype=torch.float32, device=wd)
     if bias is not None:
         b[:n] = bias.float()
     bn = pick_bn(npad, geglu)
@@ -57,7 +58,7 @@ def prep_linear(weight: torch.Tensor, bias: Optional[torch.Tensor], device, gegl
         idx = []
         for t in range(n // bn):
             idx += list(range(t * hb, (t + 1) * hb)) + list(range(half + t * hb, half + (t + 1) * hb))
-        idx = torch.tensor(idx)
+        idx = torch.tensor(idx, device=wd)
         w, b = w[idx], b[idx]
     return GemmWeight(w=w.to(device=device, dtype=torch.float16).contiguous(),
                       bias=(b.to(device) if bias is not None else None), n=npad, k=kp, cin=kp, taps=1,
@@ -70,9 +71,10 @@ def prep_conv(weight: torch.Tensor, bias: Optional[torch.Tensor], device) -> Gem
     cout, cin = weight.shape[:2]
     taps = int(torch.tensor(weight.shape[2:]).prod())
     cp, npad = _pad_to(cin, 64), _pad_to(cout, 32)
-    w = torch.zeros(npad, taps, cp, dtype=torch.float32)
+    wd = weight.device
+    w = torch.zeros(npad, taps, cp, dtype=torch.float32, device=wd)
     w[:cout, :, :cin] = weight.float().reshape(cout, cin, taps).permute(0, 2, 1)
-    b = torch.zeros(npad, dtype=torch.float32)
+    b = torch.zeros(npad, dtype=torch.float32, device=wd)
     if bias is not None:
         b[:cout] = bias.float()
     return GemmWeight(w=w.reshape(npad, taps * cp).to(device=device, dtype=torch.float16).contiguous(),

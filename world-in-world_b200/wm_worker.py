@@ -1,0 +1,343 @@
+"""Drop-in WM-server worker for the SVD-dagger ("igen") world model on the sm_100a kernels.
+
+Same process contract as the reference worker FTsvd/eval_inference.py:269-351 behind
+downstream/utils/worker_manager.py:
+  * spawned by the manager as `<python> wm_worker.py <flags...> <w_fd>` -- the LAST argv is the write-fd;
+  * CLI flags of eval_inference.py:273-294 (+ unknown `--k=v` flags the manager forwards are ignored);
+  * tasks arrive on stdin as 4-byte big-endian length + pickle of (client_id, task_id, payload);
+    results leave on <w_fd> in the same framing (worker_manager.py:186-231, 660-702);
+  * payload / result dicts: check_inputdict / check_outputdict (worker_manager.py:106-147),
+    process_input_dict / process_output_dict (downstream/api_models/__init__.py:185-237).
+Registration: point COMMON_ARGS[PLATFORM]["genex_worker"] (downstream/utils/workers_cfg.py:23-30) at this
+script -- see INTEGRATION.md.
+
+Deliberate deviations from the shipped reference, each fixing a latent defect listed in SURVEY.md section 0:
+  - world_model_name is defined ("igen", downstream/vlm.py:31) and a name sliced by the manager's Batcher
+    (worker_manager.py:457-458) is accepted when it is a prefix of it;
+  - RGBA observations are sliced to RGB (the reference pipeline fails on 4-channel PIL images);
+  - an exception inside the task is caught, logged and answered with well-formed zero frames instead of
+    killing the worker (the manager has no error channel, worker_manager.py:369-379).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import pickle
+import queue
+import sys
+import threading
+import traceback
+from typing import Callable, List, Optional
+
+import numpy as np
+import torch
+
+WORLD_MODEL_NAME = "igen"
+IGENEX_ACTION_IDS = {"forward": 1, "turn_left": 2, "turn_right": 3, "stop": 4, "placeholder": 0}
+
+
+# ----------------------------------------------------------------------------- wire format
+def read_frame(fileobj):
+    """4-byte big-endian length + pickle (worker_manager.py:218-231)."""
+    def exactly(n):
+        buf = b""
+        while len(buf) < n:
+            chunk = fileobj.read(n - len(buf))
+            if not chunk:
+                raise EOFError(f"Expected {n} bytes, got {len(buf)} before EOF.")
+            buf += chunk
+        return buf
+    n = int.from_bytes(exactly(4), "big")
+    if n > 10 ** 14:
+        raise ValueError(f"Data length {n} is too large.")
+    return pickle.loads(exactly(n))
+
+
+def write_frame(fileobj, obj) -> None:
+    """worker_manager.py:234-239."""
+    data = pickle.dumps(obj, protocol=pickle.HIGHEST_PROTOCOL)
+    fileobj.write(len(data).to_bytes(4, byteorder="big"))
+    fileobj.write(data)
+    fileobj.flush()
+
+
+def check_inputdict(d: dict) -> None:
+    """worker_manager.py:106-134 (world_model server type)."""
+    assert isinstance(d, dict)
+    missing = [k for k in ("b_action", "save_dirs", "request_model_name") if k not in d]
+    if missing:
+        raise KeyError(f"Missing required keys: {missing}.")
+    if "b_image" in d:
+        assert isinstance(d["b_image"], np.ndarray) and d["b_image"].dtype == np.uint8
+    ba = d["b_action"]
+    assert isinstance(ba, list) or (isinstance(ba, np.ndarray) and ba.dtype == np.int64)
+    assert isinstance(d["save_dirs"], list) and all(isinstance(s, str) for s in d["save_dirs"])
+    if "return_objects" in d:
+        assert isinstance(d["return_objects"], list) and all(isinstance(b, bool) for b in d["return_objects"])
+
+
+def check_outputdict(d: dict) -> None:
+    """worker_manager.py:138-147."""
+    pf = d.get("pred_frames", None)
+    assert pf is None or (isinstance(pf, np.ndarray) and pf.dtype == np.uint8)
+    assert "video_tensors" not in d
+    assert isinstance(d["save_dirs"], list)
+
+
+def worker_main(pipe_fd: int, task_fn: Callable[[dict], dict], stdin=None) -> None:
+    """Same loop as worker_manager.worker_main (:660-702): a reader thread enqueues frames from stdin, the main
+    thread runs task_fn strictly serially and writes (client_id, task_id, result) to pipe_fd; "DONE" stops it."""
+    pipe_file = os.fdopen(pipe_fd, "wb", buffering=2048 * 1024)
+    src = stdin if stdin is not None else sys.stdin.buffer
+    task_q: "queue.Queue" = queue.Queue()
+    stop = threading.Event()
+
+    def reader():
+        while not stop.is_set():
+            try:
+                item = read_frame(src)
+            except EOFError:
+                break
+            except Exception as e:          # unrecoverable read error
+                task_q.put(("ERROR", -1, {"read_error": str(e)}))
+                break
+            if isinstance(item, str) and item == "DONE":
+                break
+            task_q.put(item)
+        stop.set()
+
+    threading.Thread(target=reader, daemon=True).start()
+    while True:
+        try:
+            client_id, task_id, payload = task_q.get(timeout=0.1)
+        except queue.Empty:
+            if stop.is_set():
+                break
+            continue
+        if client_id == "ERROR":
+            print(f"[worker] receiver error: {payload}")
+            break
+        print(f"[worker] Processing task (client={client_id}, task={task_id}).  Remaining queue size: {task_q.qsize()}")
+        result = task_fn(payload)
+        check_outputdict(result)
+        write_frame(pipe_file, (client_id, task_id, result))
+    pipe_file.close()
+
+
+# ----------------------------------------------------------------------------- request helpers
+def action_ids_idx_encode(actions: np.ndarray) -> torch.Tensor:
+    """utils/svd_utils.py:594-632: A[b,i,j] = act[b,j] for j <= i else 0, column 0 forced to 'stop' (4).  int64 [b,L,L]."""
+    actions = np.asarray(actions)
+    assert actions.ndim == 2, f"Expected actions to be 2D (batch_size, sequence_length), got {actions.shape}"
+    b, L = actions.shape
+    a = actions.astype(np.int64).copy()
+    a[:, 0] = IGENEX_ACTION_IDS["stop"]
+    out = np.zeros((b, L, L), dtype=np.int64)
+    for i in range(L):
+        out[:, i, : i + 1] = a[:, : i + 1]
+    return torch.from_numpy(out)
+
+
+def name_matches(request_name, deployed: str) -> bool:
+    """api_models/__init__.py:189 with the Batcher string-slicing defect tolerated."""
+    return isinstance(request_name, str) and len(request_name) > 0 and (request_name == deployed or deployed.startswith(request_name))
+
+
+def images_to_tensor(frames_u8: np.ndarray, save_size) -> torch.Tensor:
+    """api_models/__init__.py:113-166 (center_crop=False): per frame PIL BICUBIC resize to (w_out, h_out), to_tensor.
+    frames_u8 [b, T, 3, H, W] uint8 (what the pipeline's PIL frames hold) -> float32 [b, T, 3, h_out, w_out] in [0,1]."""
+    from PIL import Image
+    b, T = frames_u8.shape[:2]
+    w_out, h_out = save_size
+    out = np.empty((b, T, 3, h_out, w_out), dtype=np.float32)
+    for i in range(b):
+        for t in range(T):
+            img = Image.fromarray(np.ascontiguousarray(frames_u8[i, t].transpose(1, 2, 0)))
+            img = img.resize((w_out, h_out), Image.BICUBIC)
+            out[i, t] = np.asarray(img, dtype=np.float32).transpose(2, 0, 1) / 255.0
+    return torch.from_numpy(out)
+
+
+def save_predict(video: np.ndarray, b_action, save_dirs: List[str]) -> None:
+    """downstream/utils/saver.py:221-274: <save_dir>/<idx>.jpg per frame + action_seq.json."""
+    from PIL import Image
+    for clip, acts, folder in zip(video, b_action, save_dirs):
+        os.makedirs(folder, exist_ok=True)
+        for i, fr in enumerate(clip):
+            Image.fromarray((np.clip(fr, 0, 1) * 255).astype(np.uint8).transpose(1, 2, 0)).save(os.path.join(folder, f"{i}.jpg"))
+        with open(os.path.join(folder, "action_seq.json"), "w") as f:
+            json.dump(acts.tolist() if hasattr(acts, "tolist") else acts, f, indent=2, ensure_ascii=False)
+
+
+# ----------------------------------------------------------------------------- the model holder
+class Navigator:
+    """Counterpart of FTsvd/eval_inference.py:85-266: owns the pipeline and a persistent, seeded generator."""
+
+    def __init__(self, args, rollout, image_encoder, vae_encoder_sd, device):
+        self.image_width, self.image_height = args.width, args.height
+        self.num_frames = args.num_frames
+        self.rollout = rollout
+        self.image_encoder = image_encoder
+        self.vae_encoder_sd = vae_encoder_sd
+        self.device = torch.device(device)
+        self.generator = torch.Generator(device=self.device).manual_seed(1)        # eval_inference.py:97
+        self.num_inference_steps = getattr(args, "num_inference_steps", 30)        # eval_inference.py:255 hard-codes 30
+        self.noise_aug_strength = 0.02
+
+    @torch.no_grad()
+    def inference(self, actions: torch.Tensor, images_u8: np.ndarray, out_width=None, out_height=None,
+                  latents: Optional[torch.Tensor] = None) -> np.ndarray:
+        """actions int64/float [b, F, F] (action_ids_idx_encode); images_u8 uint8 [b, 3, H, W].
+        Returns uint8 frames [b, F, 3, H, W] (the pipeline's PIL frames).  Branches run one after another
+        (request batch 1 per UNet call, as the reference deployment does)."""
+        from . import frontend, ops
+        from .pipeline import sample_latent_noise_
+        from .scheduler import EulerSchedule
+        dev = self.device
+        b = actions.shape[0]
+        F, H, W = self.num_frames, self.image_height, self.image_width
+        sched = EulerSchedule(self.num_inference_steps)
+        out = np.empty((b, F, 3, H, W), dtype=np.uint8)
+        img = torch.from_numpy(images_u8[:, :3]).to(dev).float() / 255.0                    # pil_to_numpy/numpy_to_pt: [0,1]
+        if img.shape[-2:] != (H, W):
+            img = torch.nn.functional.interpolate(img, size=(H, W), mode="bilinear", antialias=True)
+        emb = frontend.encode_image_clip(img, self.image_encoder)                             # [b, 1, D]
+        pre = img * 2.0 - 1.0                                                                # video_processor.preprocess
+        noise = torch.randn(pre.shape, generator=self.generator, device=dev, dtype=pre.dtype)   # pipeline :521-523
+        image_latents = frontend.vae_encode_mode(self.vae_encoder_sd, pre + self.noise_aug_strength * noise).to(torch.float16)
+        if latents is None:                                                                  # prepare_latents :325-362
+            raw = torch.randn((b, F, 4, H // 8, W // 8), generator=self.generator, device=dev, dtype=torch.float16)
+            diag = torch.diagonal(actions, dim1=-2, dim2=-1)                                 # decode_action_seq_frames :826-844
+            for i in range(b):
+                sample_latent_noise_(raw[i], diag[i])
+        else:
+            raw = latents.to(dev, torch.float16)
+        raw = raw * sched.init_noise_sigma                                                   # :361
+        for i in range(b):
+            lat = self.rollout.denoise(raw[i], image_latents[i], emb[i], actions[i].float(), num_steps=self.num_inference_steps,
+                                       noise_aug_strength=self.noise_aug_strength)
+            out[i] = self.rollout.decode(lat).cpu().numpy()
+        return out
+
+
+class WorldModelWorker:
+    """task_fn of the worker: request dict -> response dict (eval_inference.py:313-349)."""
+
+    def __init__(self, args, navigator: Navigator):
+        self.args, self.nav = args, navigator
+
+    def do_some_tasks(self, input_dict: dict) -> dict:
+        save_dirs = list(input_dict.get("save_dirs", []))
+        try:
+            check_inputdict(input_dict)
+            assert name_matches(input_dict["request_model_name"], WORLD_MODEL_NAME), \
+                f"request_model_name: {input_dict['request_model_name']} does not match deployed world_model_name: {WORLD_MODEL_NAME}"
+            b_action = np.asarray(input_dict["b_action"])
+            return_objects = bool(input_dict.get("return_objects"))
+            b_image = input_dict.get("b_image")
+            if b_image is None:
+                from PIL import Image
+                b_image = np.stack([np.asarray(Image.open(os.path.join(d, "cond_rgb.png")).convert("RGB")).transpose(2, 0, 1)
+                                    for d in save_dirs])
+            assert b_image.ndim == 4 and b_image.dtype == np.uint8, f"b_image should be uint8 B C H W, got {b_image.shape}"
+            assert len(b_action) == len(save_dirs)
+            action_ids = action_ids_idx_encode(b_action)
+            frames = self.nav.inference(action_ids, b_image, self.args.out_width, self.args.out_height)
+            video = images_to_tensor(frames, save_size=(self.args.out_width, self.args.out_height)).numpy()
+            if return_objects:
+                return {"pred_frames": (np.clip(video, 0, 1) * 255).astype(np.uint8), "save_dirs": save_dirs}
+            save_predict(video, b_action, save_dirs)
+            return {"save_dirs": save_dirs}
+        except Exception:                       # never die inside task_fn (SURVEY.md 8b "Errors")
+            traceback.print_exc()
+            n = len(save_dirs)
+            zeros = np.zeros((n, self.args.num_frames, 3, self.args.out_height, self.args.out_width), dtype=np.uint8)
+            return {"pred_frames": zeros, "save_dirs": save_dirs}
+
+
+# ----------------------------------------------------------------------------- construction
+def build_parser() -> argparse.ArgumentParser:
+    p = argparse.ArgumentParser(description="SVD-dagger world-model worker (B200 kernels)")
+    p.add_argument("--width", type=int, default=1024)
+    p.add_argument("--height", type=int, default=576)
+    p.add_argument("--out_width", type=int, default=480)
+    p.add_argument("--out_height", type=int, default=480)
+    p.add_argument("--log_dir", type=str, default="downstream/logs")
+    p.add_argument("--exp_id", type=str, default="03.15_usegenex")
+    p.add_argument("--num_frames", type=int, default=14)
+    p.add_argument("--num_past_obs", type=int, default=1)
+    p.add_argument("--task_type", type=str, default="navigation", choices=["navigation", "manipulation", "freetext"])
+    p.add_argument("--action_strategy", type=str, default="micro_cond")
+    p.add_argument("--action_input_channel", type=int, default=14)
+    p.add_argument("--device", type=str, default="cuda:0")
+    p.add_argument("--unet_path", type=str, default="")
+    p.add_argument("--svd_path", type=str, default="")
+    p.add_argument("--weight_dtype", type=str, default="float16")
+    # additions (not in the reference): synthetic weights when no checkpoint is reachable, step count, tiny geometry
+    p.add_argument("--random_init", action="store_true")
+    p.add_argument("--num_inference_steps", type=int, default=30)
+    p.add_argument("--tiny", action="store_true")
+    return p
+
+
+def build_worker(args) -> WorldModelWorker:
+    from transformers import CLIPVisionConfig, CLIPVisionModelWithProjection
+    from . import weights as W
+    from .config import TINY_UNET, TINY_VAE, UNetConfig, VAEConfig
+    from .engine import UNetEngine, VAEDecoderEngine
+    from .frontend import vae_encoder_param_spec
+    from .lib import require_device
+    from .pipeline import Rollout
+    require_device()
+    if args.num_past_obs != 1 or args.action_strategy != "micro_cond" or args.task_type != "navigation":
+        raise ValueError("this worker serves the deployed setting: micro_cond, navigation, num_past_obs == 1")
+    dev = torch.device(args.device)
+    torch.cuda.set_device(dev)
+    if args.tiny:
+        ucfg, vcfg = TINY_UNET, TINY_VAE
+        ucfg = UNetConfig(**{**ucfg.__dict__, "num_frames": args.num_frames, "action_input_channel": args.action_input_channel})
+    else:
+        ucfg = UNetConfig(num_frames=args.num_frames, action_input_channel=args.action_input_channel)
+        vcfg = VAEConfig()
+    if args.random_init or not args.unet_path:
+        usd = W.random_init_on_device(W.unet_param_spec(ucfg), 0, dev)
+        vsd = W.random_init_on_device(W.vae_decoder_param_spec(vcfg), 1, dev)
+        esd = {k: v.float() for k, v in W.random_init_on_device(
+            vae_encoder_param_spec(vcfg.block_out_channels, vcfg.layers_per_block, vcfg.latent_channels), 2, dev).items()}
+        torch.manual_seed(3)
+        clip_cfg = (CLIPVisionConfig(hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=2,
+                                     patch_size=32, projection_dim=ucfg.cross_attention_dim) if args.tiny else
+                    CLIPVisionConfig(hidden_size=1280, intermediate_size=5120, num_hidden_layers=32, num_attention_heads=16,
+                                     patch_size=14, projection_dim=1024))
+        clip = CLIPVisionModelWithProjection(clip_cfg).to(dev, torch.float16).eval()
+    else:
+        usd = W.load_safetensors_dir(args.unet_path if os.path.basename(args.unet_path.rstrip("/")) == "unet"
+                                     else os.path.join(args.unet_path, "unet"))
+        W.check_state_dict(usd, W.unet_param_spec(ucfg))
+        full_vae = W.load_safetensors_dir(os.path.join(args.svd_path, "vae"))
+        vsd = {k[len("decoder."):]: v for k, v in full_vae.items() if k.startswith("decoder.")}
+        esd = {k: v.float().to(dev) for k, v in full_vae.items() if not k.startswith("decoder.")}
+        clip = CLIPVisionModelWithProjection.from_pretrained(os.path.join(args.svd_path, "image_encoder"),
+                                                             torch_dtype=torch.float16).to(dev).eval()
+    rollout = Rollout(UNetEngine(ucfg, usd, dev), VAEDecoderEngine(vcfg, vsd, dev), dev)
+    del usd, vsd
+    return WorldModelWorker(args, Navigator(args, rollout, clip, esd, dev))
+
+
+def main(argv: List[str]) -> None:
+    pipe_fd = int(argv[-1])                                    # eval_inference.py:271
+    args, _unknown = build_parser().parse_known_args(argv[:-1])
+    print(f"[igenex worker] All Args:\n {args}")
+    worker = build_worker(args)
+    print(f"[igenex worker] Initialized navigator with device {args.device}.")
+    worker_main(pipe_fd, worker.do_some_tasks)
+
+
+if __name__ == "__main__":
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if here not in sys.path:
+        sys.path.insert(0, here)
+    import wiw_b200  # noqa: F401  (registers the package so the relative imports above resolve)
+    from wiw_b200.wm_worker import main as _main
+    _main(sys.argv[1:])
