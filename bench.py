@@ -1,0 +1,301 @@
+"""bench.py -- world-model frames/sec of the SVD-dagger rollout (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's sm_100a path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port) on host cores
+
+One "step" = one full branch rollout of BASELINE configs[1]: 576x1024 px (72x128 latents), 14 frames,
+25 Euler steps with classifier-free guidance (UNet batch 2x14) + temporal-VAE decode + uint8 quantisation,
+request batch 1 per GPU, synthetic latents / conditioning, seeded random-init weights of the full
+1.53 B-parameter architecture.  With N > 1 each rank rolls out its own planner branch (weak scaling,
+no data-path collective) and one NCCL all-gather of the decoded uint8 frames closes the step.
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+
+import numpy as np
+import torch
+
+METRIC = "world-model frames/sec (576x1024, 14-frame clip, 25 steps)"
+F, H, W = 14, 576, 1024
+h, w = H // 8, W // 8
+# algorithmic work (FlopCounterMode over the reference graph), TFLOP
+TFLOP_UNET_FWD, TFLOP_UNET_REMOVABLE, TFLOP_VAE_DEC, TFLOP_VAE_ENC = 89.604, 5.05, 97.202, 2.609
+
+
+def peaks():
+    p = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("bf16_tflops_sustained", d.get("bf16_tflops")), d.get("hbm_gbs"), "measured (MEASURED_PEAKS.json, sustained bf16)"
+    return 1590.0, 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm = sorted(int(r[1]) for r in self.rows if len(r) >= 8 and r[1].isdigit())
+        mx = [int(r[2]) for r in self.rows if len(r) >= 8 and r[2].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 8 for i in range(4) if r[4 + i].lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+# ============================================================================= CPU reference arm
+def cpu_reference_sample(steps: int, warmup: int):
+    """The reference's CPU implementation of the path = the oracle port (the vendored fork itself lives under
+    /root/reference, which does not exist on the GPU box).  Bounded sample: ONE UNet forward of the full
+    1.53 B-parameter architecture (CFG pair x 14 frames) at 8x16 latents instead of 72x128, fp32, all host
+    threads; frames/sec of the named workload is extrapolated by the algorithmic-FLOP ratio."""
+    from torch.utils.flop_counter import FlopCounterMode
+    from oracle import svd_oracle as O
+    import wiw_b200  # noqa: F401
+    from wiw_b200 import weights as Wt
+    from wiw_b200.config import FULL_UNET
+    torch.set_num_threads(os.cpu_count() or 1)
+    cores = torch.get_num_threads()
+    g = torch.Generator().manual_seed(0)
+    sd = {}
+    for name, shape in Wt.unet_param_spec(FULL_UNET):
+        fan = int(np.prod(shape[1:])) if len(shape) > 1 else 1
+        t = torch.empty(shape).normal_(0, 1, generator=g)
+        leaf = name.rsplit(".", 1)[-1]
+        sd[name] = t * (0.7 / fan ** 0.5) if (leaf == "weight" and len(shape) > 1) else (1 + 0.1 * t if leaf == "weight" else 0.05 * t)
+    cfg = O.UNetCfg()
+    sh, sw = 8, 16
+    x = torch.randn(2, F, 8, sh, sw, generator=g)
+    enc = torch.randn(2, 1, 1024, generator=g)
+    ids = torch.tensor([[6.0, 127.0, 0.02]] * 2)
+    aids = O.action_ids_idx_encode(torch.tensor([[4] + [1] * (F - 1)])).float()
+    with torch.no_grad():
+        with FlopCounterMode(display=False) as fc:
+            O.unet_forward(sd, cfg, x, torch.tensor(1.0), enc, ids, aids)
+        sample_tflop = fc.get_total_flops() / 1e12
+        for _ in range(warmup):
+            O.unet_forward(sd, cfg, x, torch.tensor(1.0), enc, ids, aids)
+        ts = []
+        for _ in range(steps):
+            t0 = time.perf_counter()
+            O.unet_forward(sd, cfg, x, torch.tensor(1.0), enc, ids, aids)
+            ts.append(time.perf_counter() - t0)
+    sec = float(np.mean(ts))
+    rate = sample_tflop / sec                                        # CPU TFLOP/s on this graph
+    clip_tflop = 25 * TFLOP_UNET_FWD + TFLOP_VAE_DEC
+    fps = F / (clip_tflop / rate)
+    return {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
+            "sample": f"1 UNet forward, full 1.53B-param arch, CFG pair x {F} frames at {sh}x{sw} latents "
+                      f"({sample_tflop:.3f} TFLOP, {sec:.2f} s => {rate:.3f} TFLOP/s fp32); frames/s extrapolated over the "
+                      f"{clip_tflop:.0f} TFLOP of one 25-step 576x1024 clip"}, sec
+
+
+def run_reference(args, rank: int, world: int):
+    if rank != 0:
+        return
+    cb, sec = cpu_reference_sample(max(1, args.steps), min(args.warmup, 1))
+    line = {"metric": METRIC, "value": cb["value"], "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "impl": "reference", "config": workload_config(world), "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(world: int) -> dict:
+    return {"workload": "BASELINE configs[1]: 576x1024 14-frame 25-step SVD UNet denoise + temporal-VAE decode, batch=1 per GPU, "
+                        "synthetic latents + random action embed", "latent": [F, 4, h, w], "inference_steps": 25, "cfg": True,
+            "branches": world, "parallelism": f"branch-sharded x{world}, one NCCL all-gather of uint8 frames" if world > 1 else "single GPU",
+            "l2": "working set (>= 165 MB per activation tensor, 3 GB weights) exceeds the 126 MB L2; no explicit flush"}
+
+
+# ============================================================================= GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="wiw", choices=["wiw", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    rank, local, world = int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch.distributed as dist
+    import wiw_b200  # noqa: F401
+    from wiw_b200 import lib as L
+    from wiw_b200 import ops
+    from wiw_b200 import weights as Wt
+    from wiw_b200.config import FULL_UNET, FULL_VAE
+    from wiw_b200.engine import UNetEngine, VAEDecoderEngine, sinusoid
+    from wiw_b200.pipeline import Rollout
+    from wiw_b200.scheduler import EulerSchedule
+    from wiw_b200 import wm_worker
+
+    L.require_device()                                   # fail loudly without the CUDA extension / a B200
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    N_STEPS = 25
+    usd = Wt.random_init_on_device(Wt.unet_param_spec(FULL_UNET), 0, dev)
+    vsd = Wt.random_init_on_device(Wt.vae_decoder_param_spec(FULL_VAE), 1, dev)
+    ro = Rollout(UNetEngine(FULL_UNET, usd, dev), VAEDecoderEngine(FULL_VAE, vsd, dev), dev)
+    del usd, vsd
+    torch.cuda.empty_cache()
+
+    # synthetic inputs of SURVEY.md section 8(d) cfg #2, one distinct branch per rank, resident in HBM
+    g = torch.Generator(device=dev).manual_seed(100 + rank)
+    sched = EulerSchedule(N_STEPS)
+    lat0 = (torch.randn(F, 4, h, w, generator=g, device=dev, dtype=torch.float16) * sched.init_noise_sigma)
+    il = torch.randn(4, h, w, generator=g, device=dev, dtype=torch.float16)
+    ie = torch.randn(1, 1024, generator=g, device=dev, dtype=torch.float16)
+    acts = np.random.default_rng(3 + rank).integers(1, 4, size=(1, F))
+    acts[0, 0] = 4
+    aids = wm_worker.action_ids_idx_encode(acts)[0].float()
+    gathered = torch.empty(world * F, 3, H, W, dtype=torch.uint8, device=dev) if world > 1 else None
+
+    def step():
+        lat = ro.denoise(lat0, il, ie, aids, num_steps=N_STEPS)
+        u8 = ro.decode(lat)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, u8)
+        return u8
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    L.COUNTERS["gpu_launches"] = 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    launches = L.COUNTERS["gpu_launches"]
+    clocks = sampler.stop() if sampler else None
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    total_ms = float(ms.item())
+    value = world * F * args.steps / (total_ms / 1e3)
+
+    # ---- stage split + roofline of the dominant kernel (conv_gemm_kernel), measured live on rank 0
+    roof, stages = None, None
+    if rank == 0:
+        def timed(fn):
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); r = fn(); b.record(); torch.cuda.synchronize()
+            return a.elapsed_time(b), r
+        x_in = torch.zeros(2 * F, h, w, 64, dtype=torch.float16, device=dev)
+        x_in[..., :8] = torch.randn(2 * F, h, w, 8, generator=g, device=dev, dtype=torch.float16)
+        t_emb = sinusoid(sched.timesteps[:1], 320).to(torch.float16).to(dev)
+        unet_ms = min(timed(lambda: ro.unet.forward(x_in, t_emb))[0] for _ in range(2))
+        lat_nhwc = ops.nchw_to_nhwc(lat0.contiguous(), 4) * 0.01
+        dec_ms = min(timed(lambda: ro.decode(lat_nhwc))[0] for _ in range(2))
+        ops.PROFILE = []
+        ro.unet.forward(x_in, t_emb)
+        torch.cuda.synchronize()
+        prof, ops.PROFILE = ops.PROFILE, None
+        g_flop = sum(p[0] for p in prof)
+        g_ms = sum(p[1].elapsed_time(p[2]) for p in prof)
+        peak, hbm, how = peaks()
+        ach = g_flop / (g_ms * 1e-3) / 1e12
+        roof = {"bound": "tensor", "kernel": "conv_gemm_kernel (tcgen05 implicit GEMM: all Linear/Conv2d/Conv3d of the UNet)",
+                "achieved": round(ach, 1), "peak": peak, "unit": "TFLOP/s", "frac": round(ach / peak, 4), "peak_source": how,
+                "launches_per_unet_forward": len(prof), "algorithmic_tflop_per_unet_forward": round(g_flop / 1e12, 3),
+                "kernel_ms_per_unet_forward": round(g_ms, 3), "share_of_unet_forward": round(g_ms / unet_ms, 3), "traffic": None}
+        stages = {"unet_forward_ms": round(unet_ms, 2), "vae_decode_ms": round(dec_ms, 2),
+                  "unet_forward_tflops": round((TFLOP_UNET_FWD - TFLOP_UNET_REMOVABLE) / unet_ms * 1e3, 1),
+                  "unet_forward_frac_of_peak": round((TFLOP_UNET_FWD - TFLOP_UNET_REMOVABLE) / unet_ms * 1e3 / peak, 4),
+                  "vae_decode_tflops": round(TFLOP_VAE_DEC / dec_ms * 1e3, 1)}
+
+    # ---- end to end through the WM-server worker API with host buffers (every rank serves its own request)
+    e2e = None
+    if not args.no_e2e:
+        wargs = wm_worker.build_parser().parse_args(["--random_init", "--device", str(dev), "--num_inference_steps", str(N_STEPS),
+                                                     "--out_width", "480", "--out_height", "480"])
+        from transformers import CLIPVisionConfig, CLIPVisionModelWithProjection
+        from wiw_b200.frontend import vae_encoder_param_spec
+        torch.manual_seed(3)
+        clip = CLIPVisionModelWithProjection(CLIPVisionConfig(hidden_size=1280, intermediate_size=5120, num_hidden_layers=32,
+                                                              num_attention_heads=16, patch_size=14, projection_dim=1024)).to(dev, torch.float16).eval()
+        esd = {k: v.float() for k, v in Wt.random_init_on_device(vae_encoder_param_spec(), 2, dev).items()}
+        worker = wm_worker.WorldModelWorker(wargs, wm_worker.Navigator(wargs, ro, clip, esd, dev))
+        rng = np.random.default_rng(7 + rank)
+        b_image = torch.from_numpy(rng.integers(0, 256, size=(1, 3, H, W), dtype=np.uint8)).pin_memory().numpy()
+        req = {"b_action": acts.astype(np.int64), "b_image": b_image, "save_dirs": [f"/tmp/wiw_bench_{rank}"],
+               "request_model_name": "igen", "return_objects": [True]}
+        out = worker.do_some_tasks(req)                               # warm-up (also primes CLIP / cuDNN autotune)
+        assert out["pred_frames"].shape == (1, F, 3, 480, 480) and out["pred_frames"].dtype == np.uint8
+        barrier()
+        t0 = time.perf_counter()
+        reps = max(1, min(args.steps, 2))
+        for _ in range(reps):
+            out = worker.do_some_tasks(req)
+        torch.cuda.synchronize()
+        dt = torch.tensor([time.perf_counter() - t0], device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * F * reps / float(dt.item()), "unit": "frames/s", "h2d_bytes_per_step": int(b_image.nbytes + acts.nbytes),
+               "d2h_bytes_per_step": int(F * 3 * H * W), "api": "wm_worker.WorldModelWorker.do_some_tasks (request dict -> pred_frames uint8)",
+               "includes": "CLIP ViT-H + fp32 VAE encode (PyTorch), 25-step rollout, decode, D2H of 576x1024 frames, PIL bicubic 480x480"}
+
+    cpu_b = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu_b, _ = cpu_reference_sample(1, 1)
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": round(value, 4), "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": round(total_ms / args.steps, 2), "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f16", "data": "synthetic", "config": workload_config(world), "clocks": clocks,
+                "e2e": e2e, "gpu_launches": launches, "roofline": roof, "stages": stages, "cpu_baseline": cpu_b}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

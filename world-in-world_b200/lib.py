@@ -67,6 +67,12 @@ SYMBOLS = {
 }
 
 
+# launch accounting for bench.py's `gpu_launches` (kernels launched by each C-ABI call)
+COUNTERS = {"gpu_launches": 0}
+KERNELS_PER_CALL = {"wiw_groupnorm": 2}
+_NO_LAUNCH = {"wiw_last_error", "wiw_abi_version", "wiw_device_ok", "wiw_groupnorm_workspace_floats"}
+
+
 def load() -> ctypes.CDLL:
     """dlopen the library (works on a CPU-only box: it does not link libcuda)."""
     global _lib
@@ -78,6 +84,13 @@ def load() -> ctypes.CDLL:
             fn = getattr(lib, name)          # AttributeError if a declared symbol is not exported
             fn.restype = res
             fn.argtypes = args
+            if name in _NO_LAUNCH:
+                continue
+
+            def counted(*a, _fn=fn, _k=KERNELS_PER_CALL.get(name, 1)):
+                COUNTERS["gpu_launches"] += _k
+                return _fn(*a)
+            setattr(lib, name, counted)
         if lib.wiw_abi_version() != ABI_VERSION:
             raise WiwError(f"ABI mismatch: library {lib.wiw_abi_version()} vs binding {ABI_VERSION}")
         _lib = lib

@@ -26,6 +26,7 @@ class GemmWeight:
     geglu: bool = False
     bn: int = 0
     n_real: int = 0          # un-padded output channels
+    k_real: int = 0          # un-padded reduction length (taps * real input channels)
 
 
 def pick_bn(n: int, geglu: bool = False) -> int:
@@ -62,7 +63,7 @@ def prep_linear(weight: torch.Tensor, bias: Optional[torch.Tensor], device, gegl
         w, b = w[idx], b[idx]
     return GemmWeight(w=w.to(device=device, dtype=torch.float16).contiguous(),
                       bias=(b.to(device) if bias is not None else None), n=npad, k=kp, cin=kp, taps=1,
-                      geglu=geglu, bn=bn, n_real=n)
+                      geglu=geglu, bn=bn, n_real=n, k_real=k)
 
 
 def prep_conv(weight: torch.Tensor, bias: Optional[torch.Tensor], device) -> GemmWeight:
@@ -78,10 +79,13 @@ def prep_conv(weight: torch.Tensor, bias: Optional[torch.Tensor], device) -> Gem
     if bias is not None:
         b[:cout] = bias.float()
     return GemmWeight(w=w.reshape(npad, taps * cp).to(device=device, dtype=torch.float16).contiguous(),
-                      bias=b.to(device), n=npad, k=taps * cp, cin=cp, taps=taps, bn=pick_bn(npad), n_real=cout)
+                      bias=b.to(device), n=npad, k=taps * cp, cin=cp, taps=taps, bn=pick_bn(npad), n_real=cout, k_real=taps * cin)
 
 
 # ----------------------------------------------------------------------------- GEMM launches
+PROFILE = None        # set to a list to record (algorithmic flops, start event, end event) per conv_gemm launch
+
+
 def _box(width: int) -> Tuple[int, int]:
     """M-tile = by rows of bx pixels (bx*by = 128); bx = largest power of two <= min(width, 128)."""
     bx = 1
@@ -120,7 +124,16 @@ def _launch(a: torch.Tensor, a_dim, a_stride, gw: GemmWeight, out: torch.Tensor,
     d.num_taps, d.chunks_per_tap = len(taps), gw.cin // 64
     for i, (cb, ox, p, oy) in enumerate(taps):
         d.tap_cbase[i], d.tap_ox[i], d.tap_p[i], d.tap_oy[i] = cb, ox, p, oy
+    if PROFILE is None:
+        L.check(lib.wiw_conv_gemm(d, L.stream_ptr()))
+        return
+    # bench.py roofline pass: CUDA events around every launch of the dominant kernel (on its own stream)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
     L.check(lib.wiw_conv_gemm(d, L.stream_ptr()))
+    e1.record()
+    rows = int(out_dim[1]) * int(out_dim[2]) * int(out_dim[3])
+    PROFILE.append((2.0 * rows * (gw.n_real or gw.n) * (gw.k_real or gw.k), e0, e1))
 
 
 def _chk(x: torch.Tensor) -> None:
