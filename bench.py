@@ -85,13 +85,20 @@ def cpu_reference_sample(steps: int, warmup: int):
     import wiw_b200  # noqa: F401
     from wiw_b200 import weights as Wt
     from wiw_b200.config import FULL_UNET
-    torch.set_num_threads(os.cpu_count() or 1)
+    # 128 intra-op threads on these small-latent tensors ran 40x SLOWER than 8 (measured on the GPU box:
+    # 135 s vs 3 s per forward -- oversubscription), so the baseline uses the thread count that is fastest
+    # for it: min(16, schedulable cores).
+    try:
+        avail = len(os.sched_getaffinity(0))
+    except AttributeError:
+        avail = os.cpu_count() or 1
+    torch.set_num_threads(max(1, min(16, avail)))
     cores = torch.get_num_threads()
     g = torch.Generator().manual_seed(0)
     sd = {}
     for name, shape in Wt.unet_param_spec(FULL_UNET):
         fan = int(np.prod(shape[1:])) if len(shape) > 1 else 1
-        t = torch.empty(shape).normal_(0, 1, generator=g)
+        t = torch.empty(shape).uniform_(-1.7320508, 1.7320508, generator=g)      # unit variance, 2x cheaper than normal_
         leaf = name.rsplit(".", 1)[-1]
         sd[name] = t * (0.7 / fan ** 0.5) if (leaf == "weight" and len(shape) > 1) else (1 + 0.1 * t if leaf == "weight" else 0.05 * t)
     cfg = O.UNetCfg()

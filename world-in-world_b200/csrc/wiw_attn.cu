@@ -3,26 +3,38 @@
 // (reference: F.scaled_dot_product_attention in AttnProcessor2_0, DP/models/attention_processor.py:2383,
 //  called from BasicTransformerBlock.attn1, DP/models/attention.py:507).
 //
-// One CTA = 128 query rows of one (image, head); two CTAs per SM overlap each other's MMA and
-// softmax phases.  Per KV tile of 128 keys:
-//   warp 0   TMA: Q once, then K_j / V_j tiles ([128][64] fp16, SWIZZLE_128B) through a 3-slot ring
-//   warp 1   tcgen05.mma: S = Q K_j^T  (M128 N128 K64, both K-major)  -> TMEM cols [0,128)
-//                         O += P_j V_j (M128 N64 K128, A = P from smem K-major, B = V MN-major) -> TMEM cols [128,192)
-//   warps 2-5 (one thread per query row): tcgen05.ld S, running max / sum, exp2, P -> fp16 smem
-//            (swizzled, A operand), lazy rescale of O in TMEM when the row max grew by > 2^8,
-//            final O / l -> fp16 -> smem -> TMA store (clipped to the image's S rows).
+// One CTA (one per SM) = 256 query rows (two 128-row tiles) of one (image, head); the two tiles
+// ping-pong so the tensor core works on one while the other is in softmax.  Per KV tile of 128 keys:
+//   warp 0     TMA: Q0,Q1 once, then K_j / V_j tiles ([128][64] fp16, SWIZZLE_128B) through a 4-slot ring
+//   warp 1     tcgen05.mma issuer: S_t = Q_t K_j^T (M128 N128 K64, K-major x K-major) -> TMEM,
+//              O_t += P_t V_j (M128 N64 K128, A = P_t from smem, B = V consumed MN-major from its TMA tile)
+//   warps 2-5  softmax of tile 0, warps 6-9 softmax of tile 1 (one thread per query row):
+//              tcgen05.ld S (2 passes: max, then exp), p = ex2.approx.f16x2 of packed fp16 exponents
+//              (half the MUFU / conversion work of an fp32 exp), P -> swizzled smem, lazy rescale of O in
+//              TMEM when some row max of the warp grew by more than 2^2, final O / l -> fp16 -> TMA store.
 #include "wiw_common.cuh"
 #include "../../include/wiw.h"
 
 namespace wiw {
 
 constexpr int kQ = 128, kKV = 128, kD = 64;
-constexpr int kTileBytes = 128 * 64 * 2;        // 16 KB: Q, K, V tiles and each half of P
-constexpr int kRing = 3;
-constexpr int kAttnThreads = 6 * 32;
-constexpr int kAttnSmem = 1024 + kTileBytes * (1 + kRing + 2) + 128;
-constexpr uint32_t kTmemCols = 256;              // S: cols [0,128), O: cols [128,192)
+constexpr int kTileBytes = 128 * 64 * 2;        // 16 KB: a Q / K / V tile and each 64-key half of P
+constexpr int kRing = 4;
+constexpr int kAttnThreads = 10 * 32;
+constexpr int kAttnSmem = 1024 + kTileBytes * (2 + kRing + 4) + 256;
+constexpr uint32_t kTmemCols = 512;              // S0 [0,128) S1 [128,256) O0 [256,320) O1 [320,384)
+constexpr float kRescaleThreshold = 2.0f;        // log2 units; keeps exponents <= 2 so fp16 exponent inputs stay fine-grained
 
+__device__ __forceinline__ uint32_t cvt_f16x2(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+__device__ __forceinline__ uint32_t ex2_f16x2(uint32_t x) {
+    uint32_t y;
+    asm("ex2.approx.f16x2 %0, %1;" : "=r"(y) : "r"(x));
+    return y;
+}
 __device__ __forceinline__ float fast_exp2(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -34,27 +46,69 @@ struct AttnArgs {
     float scale_log2;                            // (1/sqrt(d)) * log2(e)
 };
 
-__global__ void __launch_bounds__(kAttnThreads, 2)
+template <bool kMasked>
+__device__ __forceinline__ float row_max_chunk(const uint32_t* r, int base, int valid, float mx) {
+#pragma unroll
+    for (int e = 0; e < 32; e += 2) {
+        float a = __uint_as_float(r[e]), b = __uint_as_float(r[e + 1]);
+        if (kMasked) {
+            if (base + e >= valid) a = -INFINITY;
+            if (base + e + 1 >= valid) b = -INFINITY;
+        }
+        mx = fmaxf(mx, fmaxf(a, b));
+    }
+    return mx;
+}
+
+// 32 scores -> 32 fp16 probabilities written to the swizzled P tile; returns their sum
+template <bool kMasked>
+__device__ __forceinline__ float exp_chunk(const uint32_t* r, int ch, int valid, float c, float mc, uint8_t* dst, uint32_t sw) {
+    float l = 0.f;
+#pragma unroll
+    for (int v8 = 0; v8 < 4; ++v8) {
+        uint32_t p[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            float a0 = fmaf(__uint_as_float(r[v8 * 8 + 2 * e]), c, -mc);
+            float a1 = fmaf(__uint_as_float(r[v8 * 8 + 2 * e + 1]), c, -mc);
+            if (kMasked) {
+                const int k0 = ch * 32 + v8 * 8 + 2 * e;
+                if (k0 >= valid) a0 = -INFINITY;
+                if (k0 + 1 >= valid) a1 = -INFINITY;
+            }
+            p[e] = ex2_f16x2(cvt_f16x2(a0, a1));
+        }
+        const __half2 s01 = __hadd2(*reinterpret_cast<__half2*>(&p[0]), *reinterpret_cast<__half2*>(&p[1]));
+        const __half2 s23 = __hadd2(*reinterpret_cast<__half2*>(&p[2]), *reinterpret_cast<__half2*>(&p[3]));
+        const float2 f01 = __half22float2(s01), f23 = __half22float2(s23);
+        l += (f01.x + f01.y) + (f23.x + f23.y);
+        const uint32_t chunk16 = (uint32_t)((ch & 1) * 4 + v8);
+        *reinterpret_cast<uint4*>(dst + ((chunk16 ^ sw) << 4)) = make_uint4(p[0], p[1], p[2], p[3]);
+    }
+    return l;
+}
+
+__global__ void __launch_bounds__(kAttnThreads, 1)
 attn_spatial_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_out,
                     const __grid_constant__ AttnArgs a, int C) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t sQ = base;
-    const uint32_t sRing = sQ + kTileBytes;
-    const uint32_t sP = sRing + kRing * kTileBytes;              // 2 x 16 KB ([128][64] k-halves); reused for O staging
-    const uint32_t bars = sP + 2 * kTileBytes;
+    const uint32_t sQ = base;                                    // 2 tiles
+    const uint32_t sRing = sQ + 2 * kTileBytes;
+    const uint32_t sP = sRing + kRing * kTileBytes;              // tile t: 2 x 16 KB at sP + t*32 KB; reused for O staging
+    const uint32_t bars = sP + 4 * kTileBytes;
     const uint32_t bar_q = bars;
     const uint32_t bar_full = bars + 8;                          // [kRing]
     const uint32_t bar_empty = bar_full + 8 * kRing;             // [kRing]
-    const uint32_t bar_s_full = bar_empty + 8 * kRing;
-    const uint32_t bar_s_free = bar_s_full + 8;
-    const uint32_t bar_p_full = bar_s_free + 8;
-    const uint32_t bar_pv_done = bar_p_full + 8;
-    const uint32_t tmem_slot = bar_pv_done + 8;
+    const uint32_t bar_s_full = bar_empty + 8 * kRing;           // [2]
+    const uint32_t bar_s_free = bar_s_full + 16;                 // [2]
+    const uint32_t bar_p_full = bar_s_free + 16;                 // [2]
+    const uint32_t bar_pv_done = bar_p_full + 16;                // [2]
+    const uint32_t tmem_slot = bar_pv_done + 16;
     uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));       // generic pointer to `base`
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int q0 = blockIdx.x * kQ, head = blockIdx.y, img = blockIdx.z;
+    const int q0 = blockIdx.x * 2 * kQ, head = blockIdx.y, img = blockIdx.z;
     const int nkv = a.nkv;
 
     if (warp == 0 && lane == 0) {
@@ -62,10 +116,12 @@ attn_spatial_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
         tma_prefetch_desc(&tm_out);
         mbar_init(bar_q, 1);
         for (int i = 0; i < kRing; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 1); }
-        mbar_init(bar_s_full, 1);
-        mbar_init(bar_s_free, 128);
-        mbar_init(bar_p_full, 128);
-        mbar_init(bar_pv_done, 1);
+        for (int t = 0; t < 2; ++t) {
+            mbar_init(bar_s_full + 8 * t, 1);
+            mbar_init(bar_s_free + 8 * t, 128);
+            mbar_init(bar_p_full + 8 * t, 128);
+            mbar_init(bar_pv_done + 8 * t, 1);
+        }
         fence_barrier_init();
     }
     if (warp == 1) {
@@ -76,152 +132,145 @@ attn_spatial_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gen + (tmem_slot - base));
-    const uint32_t tS = tmem_base, tO = tmem_base + 128;
 
     if (warp == 0) {
+        // ================================ TMA producer ================================
         if (lane == 0) {
-            mbar_expect_tx(bar_q, kTileBytes);
+            mbar_expect_tx(bar_q, 2 * kTileBytes);
             tma_load_3d(sQ, &tm_qkv, bar_q, head * kD, q0, img);
-            for (int i = 0; i < 2 * nkv; ++i) {
+            tma_load_3d(sQ + kTileBytes, &tm_qkv, bar_q, head * kD, q0 + kQ, img);
+            for (int i = 0; i < 2 * nkv; ++i) {                 // item 2j = K_j, 2j+1 = V_j
                 const int st = i % kRing;
-                const uint32_t ph = (uint32_t)(i / kRing) & 1u;
-                mbar_wait(bar_empty + 8 * st, ph ^ 1);
+                mbar_wait(bar_empty + 8 * st, ((uint32_t)(i / kRing) & 1u) ^ 1u);
                 mbar_expect_tx(bar_full + 8 * st, kTileBytes);
-                const int j = i >> 1;
-                const int col = ((i & 1) ? 2 * C : C) + head * kD;              // even: K_j, odd: V_j
-                tma_load_3d(sRing + st * kTileBytes, &tm_qkv, bar_full + 8 * st, col, j * kKV, img);
+                const int col = ((i & 1) ? 2 * C : C) + head * kD;
+                tma_load_3d(sRing + st * kTileBytes, &tm_qkv, bar_full + 8 * st, col, (i >> 1) * kKV, img);
             }
         }
     } else if (warp == 1) {
+        // ================================ MMA issuer ================================
         if (lane == 0) {
             const uint32_t idesc_qk = make_idesc_f16(kKV, 0, 0);
             const uint32_t idesc_pv = make_idesc_f16(kD, 0, 1);               // B (= V) is MN-major
+            auto issue_qk = [&](int t, int stage) {
+                const uint64_t dq = make_desc_sw128(sQ + t * kTileBytes), dk = make_desc_sw128(sRing + stage * kTileBytes);
+#pragma unroll
+                for (int kk = 0; kk < kD / 16; ++kk)
+                    umma_f16_ss(tmem_base + t * 128, dq + 2 * kk, dk + 2 * kk, idesc_qk, kk > 0 ? 1u : 0u);
+                umma_commit(bar_s_full + 8 * t);
+            };
+            auto issue_pv = [&](int t, int stage, bool first) {
+                const uint64_t dv = make_desc_sw128(sRing + stage * kTileBytes);
+#pragma unroll
+                for (int kk = 0; kk < kKV / 16; ++kk) {
+                    const uint64_t dp = make_desc_sw128(sP + t * 2 * kTileBytes + (kk >> 2) * kTileBytes) + 2 * (kk & 3);
+                    umma_f16_ss(tmem_base + 256 + t * 64, dp, dv + (uint64_t)kk * (2048 >> 4), idesc_pv, (!first || kk > 0) ? 1u : 0u);
+                }
+                umma_commit(bar_pv_done + 8 * t);
+            };
             mbar_wait(bar_q, 0);
+            mbar_wait(bar_full + 0, 0);                                       // K_0 in ring slot 0
+            tc_fence_after();
+            issue_qk(0, 0);
+            issue_qk(1, 0);
+            umma_commit(bar_empty + 0);
             for (int j = 0; j < nkv; ++j) {
-                // ---- S = Q K_j^T
-                int i = 2 * j, st = i % kRing;
-                mbar_wait(bar_full + 8 * st, (uint32_t)(i / kRing) & 1u);
-                if (j > 0) mbar_wait(bar_s_free, (uint32_t)(j - 1) & 1u);     // softmax finished reading S_{j-1}
-                tc_fence_after();
-                {
-                    const uint64_t dq = make_desc_sw128(sQ), dk = make_desc_sw128(sRing + st * kTileBytes);
-#pragma unroll
-                    for (int kk = 0; kk < kD / 16; ++kk) umma_f16_ss(tS, dq + 2 * kk, dk + 2 * kk, idesc_qk, kk > 0 ? 1u : 0u);
-                }
-                umma_commit(bar_empty + 8 * st);
-                umma_commit(bar_s_full);
-                // ---- O += P_j V_j
-                i = 2 * j + 1; st = i % kRing;
-                mbar_wait(bar_full + 8 * st, (uint32_t)(i / kRing) & 1u);
-                mbar_wait(bar_p_full, (uint32_t)j & 1u);
-                tc_fence_after();
-                {
-                    const uint64_t dv = make_desc_sw128(sRing + st * kTileBytes);
-#pragma unroll
-                    for (int kk = 0; kk < kKV / 16; ++kk) {
-                        const uint64_t dp = make_desc_sw128(sP + (kk >> 2) * kTileBytes) + 2 * (kk & 3);
-                        umma_f16_ss(tO, dp, dv + (uint64_t)kk * (2048 >> 4), idesc_pv, (j > 0 || kk > 0) ? 1u : 0u);
+                const bool more = (j + 1 < nkv);
+                const int ik = 2 * j + 2, iv = 2 * j + 1;
+                const int sk = ik % kRing, sv = iv % kRing;
+                if (more) mbar_wait(bar_full + 8 * sk, (uint32_t)(ik / kRing) & 1u);      // K_{j+1}
+                mbar_wait(bar_full + 8 * sv, (uint32_t)(iv / kRing) & 1u);                // V_j
+                for (int t = 0; t < 2; ++t) {
+                    if (more) {
+                        mbar_wait(bar_s_free + 8 * t, (uint32_t)j & 1u);      // softmax t finished reading S_t of tile j
+                        tc_fence_after();
+                        issue_qk(t, sk);
                     }
+                    mbar_wait(bar_p_full + 8 * t, (uint32_t)j & 1u);          // P_t of tile j is in smem
+                    tc_fence_after();
+                    issue_pv(t, sv, j == 0);
                 }
-                umma_commit(bar_empty + 8 * st);
-                umma_commit(bar_pv_done);
+                if (more) umma_commit(bar_empty + 8 * sk);
+                umma_commit(bar_empty + 8 * sv);
             }
         }
     } else {
-        // ================= softmax / correction / epilogue: one thread per query row =================
+        // ================= softmax / correction / epilogue: one thread per query row of tile t =================
+        const int t = (warp - 2) >> 2;
         const int qd = warp & 3;
         const int row = qd * 32 + lane;
         const uint32_t lane_sel = (uint32_t)(qd * 32) << 16;
+        const uint32_t tS = tmem_base + t * 128 + lane_sel, tO = tmem_base + 256 + t * 64 + lane_sel;
         const uint32_t sw = (uint32_t)row & 7u;
-        uint8_t* pP = gen + (sP - base) + row * 128;
+        uint8_t* pP = gen + (sP - base) + t * 2 * kTileBytes + row * 128;
         float m_ref = -INFINITY, l = 0.f;
         const float c = a.scale_log2;
         for (int j = 0; j < nkv; ++j) {
-            const int valid = min(kKV, a.S - j * kKV);              // keys beyond S are zero-filled: mask them
-            mbar_wait(bar_s_full, (uint32_t)j & 1u);
+            const int valid = a.S - j * kKV;                       // keys beyond S are zero-filled by TMA: mask them
+            const bool masked = valid < kKV;
+            mbar_wait(bar_s_full + 8 * t, (uint32_t)j & 1u);
             tc_fence_after();
             // pass 1: row max
             float mx = -INFINITY;
 #pragma unroll
             for (int ch = 0; ch < 4; ++ch) {
                 uint32_t r[32];
-                tmem_ld_32x32b_x32(tS + lane_sel + ch * 32, r);
+                tmem_ld_32x32b_x32(tS + ch * 32, r);
                 tmem_ld_wait();
-#pragma unroll
-                for (int e = 0; e < 32; ++e) {
-                    const float s = (ch * 32 + e < valid) ? __uint_as_float(r[e]) : -INFINITY;
-                    mx = fmaxf(mx, s);
-                }
+                mx = masked ? row_max_chunk<true>(r, ch * 32, valid, mx) : row_max_chunk<false>(r, ch * 32, valid, mx);
             }
-            // lazy rescale: keep exponent reference m_ref unless some row of the warp grew by > 8 (log2 units)
             float alpha = 1.f;
-            const bool grow = (mx - m_ref) * c > 8.0f;
-            const bool any_grow = __any_sync(0xffffffffu, grow || (j == 0));
+            const bool grow = (mx - m_ref) * c > kRescaleThreshold;
+            const bool any_grow = __any_sync(0xffffffffu, grow) || (j == 0);
             if (any_grow) {
                 const float m_new = fmaxf(m_ref, mx);
-                alpha = (m_ref == -INFINITY) ? 0.f : exp2f((m_ref - m_new) * c);
+                alpha = (m_ref == -INFINITY) ? 0.f : fast_exp2((m_ref - m_new) * c);
                 m_ref = m_new;
                 l *= alpha;
             }
             if (j > 0) {
-                // P buffer and O are owned by the tensor core until PV_{j-1} has retired
-                mbar_wait(bar_pv_done, (uint32_t)(j - 1) & 1u);
+                // the P_t buffer and O_t belong to the tensor core until PV of tile j-1 has retired
+                mbar_wait(bar_pv_done + 8 * t, (uint32_t)(j - 1) & 1u);
                 tc_fence_after();
                 if (any_grow) {
 #pragma unroll
                     for (int ch = 0; ch < 4; ++ch) {
                         uint32_t r[16];
-                        tmem_ld_32x32b_x16(tO + lane_sel + ch * 16, r);
+                        tmem_ld_32x32b_x16(tO + ch * 16, r);
                         tmem_ld_wait();
 #pragma unroll
                         for (int e = 0; e < 16; ++e) r[e] = __float_as_uint(__uint_as_float(r[e]) * alpha);
-                        tmem_st_32x32b_x16(tO + lane_sel + ch * 16, r);
+                        tmem_st_32x32b_x16(tO + ch * 16, r);
                     }
                     tmem_st_wait();
                 }
             }
-            // pass 2: p = exp2((s - m_ref) * c) -> fp16 -> P smem (K-major, SWIZZLE_128B, two 64-key halves)
+            // pass 2: p = 2^((s - m_ref) * c) in packed fp16 -> P smem (K-major, SWIZZLE_128B, two 64-key halves)
             const float mc = m_ref * c;
 #pragma unroll
             for (int ch = 0; ch < 4; ++ch) {
                 uint32_t r[32];
-                tmem_ld_32x32b_x32(tS + lane_sel + ch * 32, r);
+                tmem_ld_32x32b_x32(tS + ch * 32, r);
                 tmem_ld_wait();
-                if (ch == 3) {                                   // last read of S_j: release it for QK_{j+1}
+                if (ch == 3) {                                   // last read of S_t: release it for the next QK
                     tc_fence_before();
-                    mbar_arrive(bar_s_free);
+                    mbar_arrive(bar_s_free + 8 * t);
                 }
                 uint8_t* dst = pP + (ch >> 1) * kTileBytes;
-#pragma unroll
-                for (int v8 = 0; v8 < 4; ++v8) {
-                    uint4 u;
-                    __half2* hh = reinterpret_cast<__half2*>(&u);
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const int k0 = ch * 32 + v8 * 8 + 2 * e;
-                        float p0 = (k0 < valid) ? fast_exp2(__uint_as_float(r[v8 * 8 + 2 * e]) * c - mc) : 0.f;
-                        float p1 = (k0 + 1 < valid) ? fast_exp2(__uint_as_float(r[v8 * 8 + 2 * e + 1]) * c - mc) : 0.f;
-                        hh[e] = __floats2half2_rn(p0, p1);
-                        const float2 back = __half22float2(hh[e]);   // sum what the tensor core will see
-                        l += back.x + back.y;
-                    }
-                    const uint32_t chunk16 = (uint32_t)((ch & 1) * 4 + v8);
-                    *reinterpret_cast<uint4*>(dst + ((chunk16 ^ sw) << 4)) = u;
-                }
+                l += masked ? exp_chunk<true>(r, ch, valid, c, mc, dst, sw) : exp_chunk<false>(r, ch, valid, c, mc, dst, sw);
             }
             fence_proxy_async_smem();
             tc_fence_before();
-            mbar_arrive(bar_p_full);
+            mbar_arrive(bar_p_full + 8 * t);
         }
-        // ---- epilogue: O / l -> fp16 -> smem (SW128) -> TMA store
-        mbar_wait(bar_pv_done, (uint32_t)(nkv - 1) & 1u);
+        // ---- epilogue: O / l -> fp16 -> smem (SW128, first half of this tile's P buffer) -> TMA store
+        mbar_wait(bar_pv_done + 8 * t, (uint32_t)(nkv - 1) & 1u);
         tc_fence_after();
         const float inv = 1.f / l;
-        uint8_t* dst = gen + (sP - base) + row * 128;
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch) {
             uint32_t r[16];
-            tmem_ld_32x32b_x16(tO + lane_sel + ch * 16, r);
+            tmem_ld_32x32b_x16(tO + ch * 16, r);
             tmem_ld_wait();
 #pragma unroll
             for (int v8 = 0; v8 < 2; ++v8) {
@@ -231,15 +280,16 @@ attn_spatial_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
                 for (int e = 0; e < 4; ++e)
                     hh[e] = __floats2half2_rn(__uint_as_float(r[v8 * 8 + 2 * e]) * inv, __uint_as_float(r[v8 * 8 + 2 * e + 1]) * inv);
                 const uint32_t chunk16 = (uint32_t)(ch * 2 + v8);
-                *reinterpret_cast<uint4*>(dst + ((chunk16 ^ sw) << 4)) = u;
+                *reinterpret_cast<uint4*>(pP + ((chunk16 ^ sw) << 4)) = u;
             }
         }
         fence_proxy_async_smem();
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (warp == 2 && lane == 0) {
+        if (t == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+        else        asm volatile("bar.sync 2, 128;" ::: "memory");
+        if (qd == 2 && lane == 0) {                              // first warp of each softmax group (warps 2 and 6)
             asm volatile(
                 "cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
-                ::"l"(reinterpret_cast<uint64_t>(&tm_out)), "r"(sP), "r"(head * kD), "r"(q0), "r"(img) : "memory");
+                ::"l"(reinterpret_cast<uint64_t>(&tm_out)), "r"(sP + t * 2 * kTileBytes), "r"(head * kD), "r"(q0 + t * kQ), "r"(img) : "memory");
             tma_store_commit();
             tma_store_wait_all<0>();
         }
@@ -283,7 +333,7 @@ extern "C" int wiw_attention_spatial(const void* qkv, void* out, int images, int
         WIW_CHECK_CUDA(cudaFuncSetAttribute(attn_spatial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
         attr_set = true;
     }
-    dim3 grid((S + kQ - 1) / kQ, C / 64, images);
+    dim3 grid((S + 2 * kQ - 1) / (2 * kQ), C / 64, images);
     attn_spatial_kernel<<<grid, kAttnThreads, kAttnSmem, stream>>>(tm_qkv, tm_out, a, C);
     WIW_CHECK_CUDA(cudaGetLastError());
     return 0;
