@@ -7,8 +7,9 @@
 //   warp 1      MMA issuer: tcgen05.mma cta_group::1 kind::f16, M=128, N=bn, K=16 x4 per stage,
 //               fp32 accumulators in TMEM, double-buffered across tiles
 //   warp 2      TMEM allocator + TMA loader of the epilogue's residual / aux tiles
-//   warps 3-6   epilogue: tcgen05.ld -> (bias, per-row-group table, GEGLU, residual blend) -> fp16
-//               -> swizzled smem -> TMA store (clips partial tiles)
+//   warps 3-10  epilogue, two groups of 4 warps on alternating 32-column chunks: tcgen05.ld -> (bias,
+//               per-row-group table, SiLU, GEGLU, residual blend) -> fp16 -> swizzled smem -> TMA store
+//               (clips partial tiles)
 //
 // Pipelines: smem full/empty ring (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue),
 // residual full/empty ring (loader <-> epilogue), bulk-group ring for the stores.
@@ -21,10 +22,10 @@ constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;                    // 64 fp16 = one 128-byte swizzle row
 constexpr int kEpiCols = 32;                   // epilogue chunk: 32 fp16 = 64-byte rows (SWIZZLE_64B)
 constexpr int kEpiChunkBytes = kBlockM * kEpiCols * 2;   // 8 KB
-constexpr int kOutBufs = 3;
+constexpr int kOutBufs = 4;                    // 2 per epilogue group
 constexpr int kResSlots = 4;
 constexpr int kMaxStages = 8;
-constexpr int kThreads = 7 * 32;
+constexpr int kThreads = 11 * 32;              // TMA, MMA, epilogue loader, 2 x 4 epilogue warps
 constexpr int kSmemBudget = 227 * 1024;
 
 struct GemmArgs {
@@ -99,7 +100,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(bar_tfull + 8 * i, 1);
-            mbar_init(bar_tempty + 8 * i, 128);
+            mbar_init(bar_tempty + 8 * i, 256);
         }
         for (int i = 0; i < kResSlots; ++i) {
             mbar_init(bar_rfull + 8 * i, 1);
@@ -190,19 +191,23 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             }
         }
     } else {
-        // ================================ epilogue (warps 3..6) ================================
+        // ================================ epilogue (warps 3..10, two groups of 4) ================================
+        // Group grp handles the 32-column chunks j with j % 2 == grp; both groups read the same TMEM lanes
+        // (a warp may only touch lane quadrant warp % 4).  Two warps per SM sub-partition hide each other's
+        // TMEM-load / barrier / store latency.
+        const int grp = (warp - 3) >> 2;
         const int q = warp & 3;                        // TMEM lane quadrant this warp may access
         const int row = q * 32 + lane;                 // row of the 128-row tile == TMEM lane
-        const bool store_leader = (warp == 3 && lane == 0);
+        const bool store_leader = (((warp - 3) & 3) == 0 && lane == 0);
         const int chunks = g.out_cols_per_tile / kEpiCols;
         const uint32_t sw = (uint32_t(row) >> 1) & 3u;  // SWIZZLE_64B: 16-B chunk index ^= (row>>1)&3
         const uint32_t row_off = uint32_t(row) * 64u;
+        const uint32_t bar_id = 1 + grp;
         int as = 0;
         uint32_t aph = 0;
-        int rs = 0;
-        uint32_t rph = 0;
-        int ob = 0;
-        for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
+        int ob = 0;                                    // this group's staging buffer (2 per group)
+        long long chunk_base = 0;                      // chunks consumed by this CTA before the current tile
+        for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, chunk_base += chunks) {
             const TileCoord t = decode_tile(g, tile);
             const int acc_n0 = t.n_tile * g.bn;                       // first GEMM column of this tile
             const int out_c0 = t.n_tile * g.out_cols_per_tile;        // first output channel
@@ -217,7 +222,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             mbar_wait(bar_tfull + 8 * as, aph);
             tc_fence_after();
             const uint32_t t_acc = tmem_base + as * acc_stride + (uint32_t(q * 32) << 16);
-            for (int j = 0; j < chunks; ++j) {
+            const int last_j = ((chunks - 1 - grp) >= 0) ? (grp + 2 * ((chunks - 1 - grp) / 2)) : -1;
+            if (last_j < 0) {                          // nothing to do for this group in this tile
+                tc_fence_before();
+                mbar_arrive(bar_tempty + 8 * as);
+            }
+            for (int j = grp; j < chunks; j += 2) {
                 float v[kEpiCols];
                 {
                     uint32_t r[kEpiCols];
@@ -259,14 +269,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 #pragma unroll
                     for (int c = 0; c < kEpiCols; c += 4) {
                         const float4 b4 = (g.bias != nullptr) ? __ldg(reinterpret_cast<const float4*>(g.bias + nb + c)) : make_float4(0, 0, 0, 0);
-                        v[c] *= gelu_erf_f(__uint_as_float(r[c]) + b4.x);
-                        v[c + 1] *= gelu_erf_f(__uint_as_float(r[c + 1]) + b4.y);
-                        v[c + 2] *= gelu_erf_f(__uint_as_float(r[c + 2]) + b4.z);
-                        v[c + 3] *= gelu_erf_f(__uint_as_float(r[c + 3]) + b4.w);
+                        v[c] *= gelu_fast_f(__uint_as_float(r[c]) + b4.x);
+                        v[c + 1] *= gelu_fast_f(__uint_as_float(r[c + 1]) + b4.y);
+                        v[c + 2] *= gelu_fast_f(__uint_as_float(r[c + 2]) + b4.z);
+                        v[c + 3] *= gelu_fast_f(__uint_as_float(r[c + 3]) + b4.w);
                     }
                 }
-                if (j == chunks - 1) {
-                    // all TMEM reads of this accumulator stage are done: hand it back to the MMA warp
+                if (j == last_j) {
+                    // this group's TMEM reads of the accumulator stage are done: hand it back to the MMA warp
                     tc_fence_before();
                     mbar_arrive(bar_tempty + 8 * as);
                 }
@@ -275,6 +285,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                     for (int c = 0; c < kEpiCols; ++c) v[c] *= g.s_acc;
                 }
                 if (has_epi_loads) {
+                    const long long n = chunk_base + j;                       // global chunk index of this CTA
+                    const int rs = int(n % kResSlots);
+                    const uint32_t rph = uint32_t(n / kResSlots) & 1u;
                     mbar_wait(bar_rfull + 8 * rs, rph);
                     const uint8_t* gen = smem_raw + (res_base - smem_u32(smem_raw));
                     if (g.has_res) {
@@ -306,11 +319,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                         }
                     }
                     mbar_arrive(bar_rempty + 8 * rs);
-                    if (++rs == kResSlots) { rs = 0; rph ^= 1; }
                 }
-                // fp16 -> swizzled staging buffer `ob`
+                // The store issued two chunks ago by this group read the buffer we are about to overwrite:
+                // the leader waits until at most one of its bulk groups is still reading, then releases the group.
+                if (store_leader) tma_store_wait_read<1>();
+                asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
                 {
-                    uint8_t* p = smem_raw + (out_base - smem_u32(smem_raw)) + ob * kEpiChunkBytes + row_off;
+                    uint8_t* p = smem_raw + (out_base - smem_u32(smem_raw)) + (grp * 2 + ob) * kEpiChunkBytes + row_off;
 #pragma unroll
                     for (int c4 = 0; c4 < 4; ++c4) {
                         uint4 u;
@@ -321,16 +336,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                     }
                 }
                 fence_proxy_async_smem();
-                // The leader makes sure the store that last used the NEXT buffer has finished reading
-                // it (<= 1 group may stay in flight), so this single barrier both publishes chunk j
-                // and frees the buffer chunk j+1 will write.
-                if (store_leader) tma_store_wait_read<1>();
-                asm volatile("bar.sync 1, 128;" ::: "memory");
+                asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
                 if (store_leader) {
-                    tma_store_4d(&tm_out, out_base + ob * kEpiChunkBytes, out_c0 + j * kEpiCols, t.x0, t.y0, t.img);
+                    tma_store_4d(&tm_out, out_base + (grp * 2 + ob) * kEpiChunkBytes, out_c0 + j * kEpiCols, t.x0, t.y0, t.img);
                     tma_store_commit();
                 }
-                if (++ob == kOutBufs) ob = 0;
+                ob ^= 1;
             }
             if (++as == 2) { as = 0; aph ^= 1; }
         }
