@@ -69,7 +69,7 @@ SYMBOLS = {
 
 # launch accounting for bench.py's `gpu_launches` (kernels launched by each C-ABI call)
 COUNTERS = {"gpu_launches": 0}
-KERNELS_PER_CALL = {"wiw_groupnorm": 2}
+KERNELS_PER_CALL = {"wiw_groupnorm": 3}
 _NO_LAUNCH = {"wiw_last_error", "wiw_abi_version", "wiw_device_ok", "wiw_groupnorm_workspace_floats"}
 
 
