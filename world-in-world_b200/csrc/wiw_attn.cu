@@ -9,9 +9,10 @@
 //   warp 1     tcgen05.mma issuer: S_t = Q_t K_j^T (M128 N128 K64, K-major x K-major) -> TMEM,
 //              O_t += P_t V_j (M128 N64 K128, A = P_t from smem, B = V consumed MN-major from its TMA tile)
 //   warps 2-5  softmax of tile 0, warps 6-9 softmax of tile 1 (one thread per query row):
-//              tcgen05.ld S (2 passes: max, then exp), p = ex2.approx.f16x2 of packed fp16 exponents
-//              (half the MUFU / conversion work of an fp32 exp), P -> swizzled smem, lazy rescale of O in
-//              TMEM when some row max of the warp grew by more than 2^2, final O / l -> fp16 -> TMA store.
+//              tcgen05.ld S (2 passes: max, then exp2), P -> fp16 -> swizzled smem, lazy rescale of O in TMEM
+//              when some row max of the warp grew by more than 2^8.  The row sum l is NOT accumulated by the
+//              softmax threads: the PV MMA runs with N = 80 where B columns 64..79 come from a tile of ones, so
+//              O[:, 64] = sum_k P[:, k] in fp32 for free.  Final O / l -> fp16 -> TMA store.
 #include "wiw_common.cuh"
 #include "../../include/wiw.h"
 
@@ -21,9 +22,10 @@ constexpr int kQ = 128, kKV = 128, kD = 64;
 constexpr int kTileBytes = 128 * 64 * 2;        // 16 KB: a Q / K / V tile and each 64-key half of P
 constexpr int kRing = 4;
 constexpr int kAttnThreads = 10 * 32;
-constexpr int kAttnSmem = 1024 + kTileBytes * (2 + kRing + 4) + 256;
-constexpr uint32_t kTmemCols = 512;              // S0 [0,128) S1 [128,256) O0 [256,320) O1 [320,384)
-constexpr float kRescaleThreshold = 2.0f;        // log2 units; keeps exponents <= 2 so fp16 exponent inputs stay fine-grained
+constexpr int kAttnSmem = 1024 + kTileBytes * (2 + kRing + 1 + 4) + 256;   // Q0,Q1 | K/V ring | ones | P0,P1
+constexpr uint32_t kTmemCols = 512;              // S0 [0,128) S1 [128,256) O0 [256,336) O1 [384,464)
+constexpr int kOCols = 80;                       // 64 output columns + 16 copies of the row sum l (P @ ones)
+constexpr float kRescaleThreshold = 8.0f;        // log2 units (P <= 2^8 fits fp16 comfortably)
 
 __device__ __forceinline__ uint32_t cvt_f16x2(float lo, float hi) {
     uint32_t r;
@@ -50,54 +52,42 @@ __device__ __forceinline__ float exp2_poly(float x) {
     const float p = fmaf(fmaf(fmaf(0.05517167f, f, 0.24261113f), f, 0.69326097f), f, 0.99992806f);
     return __int_as_float(__float_as_int(p) + (__float_as_int(xr) << 23));
 }
-constexpr int kPolyPairs = 1;                          // of every 4 (pairs of) exponentials, this many use exp2_poly
+constexpr int kPolyPairs = 0;                          // of every 4 (pairs of) exponentials, this many use exp2_poly
 
 struct AttnArgs {
     int S, nkv;
     float scale_log2;                            // (1/sqrt(d)) * log2(e)
 };
 
-template <bool kMasked>
-__device__ __forceinline__ float row_max_chunk(const uint32_t* r, int base, int valid, float mx) {
+// keys at or beyond `valid` (zero-filled by TMA past the image's S rows) -> -inf before max / exp
+__device__ __forceinline__ void mask_chunk(uint32_t* r, int base, int valid) {
 #pragma unroll
-    for (int e = 0; e < 32; e += 2) {
-        float a = __uint_as_float(r[e]), b = __uint_as_float(r[e + 1]);
-        if (kMasked) {
-            if (base + e >= valid) a = -INFINITY;
-            if (base + e + 1 >= valid) b = -INFINITY;
-        }
-        mx = fmaxf(mx, fmaxf(a, b));
-    }
+    for (int e = 0; e < 32; ++e)
+        if (base + e >= valid) r[e] = 0xff800000u;
+}
+
+__device__ __forceinline__ float row_max_chunk(const uint32_t* r, float mx) {
+#pragma unroll
+    for (int e = 0; e < 32; e += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(r[e]), __uint_as_float(r[e + 1])));
     return mx;
 }
 
-// 32 scores -> 32 fp16 probabilities written to the swizzled P tile; returns their sum
-template <bool kMasked>
-__device__ __forceinline__ float exp_chunk(const uint32_t* r, int ch, int valid, float c, float mc, uint8_t* dst, uint32_t sw) {
-    float l = 0.f;
+// 32 scores -> 32 fp16 probabilities p = 2^(s*c - mc) written to the swizzled P tile
+// (fp32 MUFU.EX2 + one F2FP pack per pair: cheaper than ex2.f16x2, which splits into two MUFU + a PRMT)
+__device__ __forceinline__ void exp_chunk(const uint32_t* r, int ch, float c, float mc, uint8_t* dst, uint32_t sw) {
 #pragma unroll
     for (int v8 = 0; v8 < 4; ++v8) {
         uint32_t p[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-            float a0 = fmaf(__uint_as_float(r[v8 * 8 + 2 * e]), c, -mc);
-            float a1 = fmaf(__uint_as_float(r[v8 * 8 + 2 * e + 1]), c, -mc);
-            if (kMasked) {
-                const int k0 = ch * 32 + v8 * 8 + 2 * e;
-                if (k0 >= valid) a0 = -INFINITY;
-                if (k0 + 1 >= valid) a1 = -INFINITY;
-            }
-            if (!kMasked && e < kPolyPairs) p[e] = cvt_f16x2(exp2_poly(a0), exp2_poly(a1));
-            else p[e] = ex2_f16x2(cvt_f16x2(a0, a1));
+            const float a0 = fmaf(__uint_as_float(r[v8 * 8 + 2 * e]), c, -mc);
+            const float a1 = fmaf(__uint_as_float(r[v8 * 8 + 2 * e + 1]), c, -mc);
+            if (e < kPolyPairs) p[e] = cvt_f16x2(exp2_poly(a0), exp2_poly(a1));
+            else p[e] = cvt_f16x2(fast_exp2(a0), fast_exp2(a1));
         }
-        const __half2 s01 = __hadd2(*reinterpret_cast<__half2*>(&p[0]), *reinterpret_cast<__half2*>(&p[1]));
-        const __half2 s23 = __hadd2(*reinterpret_cast<__half2*>(&p[2]), *reinterpret_cast<__half2*>(&p[3]));
-        const float2 f01 = __half22float2(s01), f23 = __half22float2(s23);
-        l += (f01.x + f01.y) + (f23.x + f23.y);
         const uint32_t chunk16 = (uint32_t)((ch & 1) * 4 + v8);
         *reinterpret_cast<uint4*>(dst + ((chunk16 ^ sw) << 4)) = make_uint4(p[0], p[1], p[2], p[3]);
     }
-    return l;
 }
 
 __global__ void __launch_bounds__(kAttnThreads, 1)
@@ -107,7 +97,8 @@ attn_spatial_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t sQ = base;                                    // 2 tiles
     const uint32_t sRing = sQ + 2 * kTileBytes;
-    const uint32_t sP = sRing + kRing * kTileBytes;              // tile t: 2 x 16 KB at sP + t*32 KB; reused for O staging
+    const uint32_t sOnes = sRing + kRing * kTileBytes;           // [128][64] fp16 ones: the extra N-atom of the PV B operand
+    const uint32_t sP = sOnes + kTileBytes;                      // tile t: 2 x 16 KB at sP + t*32 KB; reused for O staging
     const uint32_t bars = sP + 4 * kTileBytes;
     const uint32_t bar_q = bars;
     const uint32_t bar_full = bars + 8;                          // [kRing]
@@ -140,6 +131,9 @@ attn_spatial_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
         tmem_alloc(tmem_slot, kTmemCols);
         tmem_relinquish();
     }
+    for (int i = threadIdx.x; i < kTileBytes / 16; i += kAttnThreads)
+        *reinterpret_cast<uint4*>(gen + (sOnes - base) + i * 16) = make_uint4(0x3C003C00u, 0x3C003C00u, 0x3C003C00u, 0x3C003C00u);
+    fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -163,7 +157,7 @@ attn_spatial_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
         // ================================ MMA issuer ================================
         if (lane == 0) {
             const uint32_t idesc_qk = make_idesc_f16(kKV, 0, 0);
-            const uint32_t idesc_pv = make_idesc_f16(kD, 0, 1);               // B (= V) is MN-major
+            const uint32_t idesc_pv = make_idesc_f16(kOCols, 0, 1);           // B (= [V | ones]) is MN-major, N = 80
             auto issue_qk = [&](int t, int stage) {
                 const uint64_t dq = make_desc_sw128(sQ + t * kTileBytes), dk = make_desc_sw128(sRing + stage * kTileBytes);
 #pragma unroll
@@ -172,11 +166,15 @@ attn_spatial_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
                 umma_commit(bar_s_full + 8 * t);
             };
             auto issue_pv = [&](int t, int stage, bool first) {
-                const uint64_t dv = make_desc_sw128(sRing + stage * kTileBytes);
+                // MN-major B: N-atom 0 (columns 0..63) = the V tile, N-atom 1 (columns 64..79) = the ones tile at +LBO;
+                // K groups of 8 rows at SBO = 1024 B.  O[:, 64..79] therefore accumulates the row sums of P in fp32.
+                const uint32_t v_addr = sRing + stage * kTileBytes;
+                const uint64_t dv = (uint64_t((v_addr & 0x3FFFF) >> 4)) | (uint64_t((sOnes - v_addr) >> 4) << 16) |
+                                    (uint64_t(1024 >> 4) << 32) | (uint64_t(1) << 46) | (uint64_t(2) << 61);
 #pragma unroll
                 for (int kk = 0; kk < kKV / 16; ++kk) {
                     const uint64_t dp = make_desc_sw128(sP + t * 2 * kTileBytes + (kk >> 2) * kTileBytes) + 2 * (kk & 3);
-                    umma_f16_ss(tmem_base + 256 + t * 64, dp, dv + (uint64_t)kk * (2048 >> 4), idesc_pv, (!first || kk > 0) ? 1u : 0u);
+                    umma_f16_ss(tmem_base + 256 + t * 128, dp, dv + (uint64_t)kk * (2048 >> 4), idesc_pv, (!first || kk > 0) ? 1u : 0u);
                 }
                 umma_commit(bar_pv_done + 8 * t);
             };
@@ -212,24 +210,41 @@ attn_spatial_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
         const int qd = warp & 3;
         const int row = qd * 32 + lane;
         const uint32_t lane_sel = (uint32_t)(qd * 32) << 16;
-        const uint32_t tS = tmem_base + t * 128 + lane_sel, tO = tmem_base + 256 + t * 64 + lane_sel;
+        const uint32_t tS = tmem_base + t * 128 + lane_sel, tO = tmem_base + 256 + t * 128 + lane_sel;
         const uint32_t sw = (uint32_t)row & 7u;
         uint8_t* pP = gen + (sP - base) + t * 2 * kTileBytes + row * 128;
-        float m_ref = -INFINITY, l = 0.f;
+        float m_ref = -INFINITY;
         const float c = a.scale_log2;
         for (int j = 0; j < nkv; ++j) {
             const int valid = a.S - j * kKV;                       // keys beyond S are zero-filled by TMA: mask them
             const bool masked = valid < kKV;
             mbar_wait(bar_s_full + 8 * t, (uint32_t)j & 1u);
             tc_fence_after();
-            // pass 1: row max
+            // pass 1: row max.  The TMEM load of chunk ch+1 is in flight while chunk ch is reduced.
             float mx = -INFINITY;
-#pragma unroll
-            for (int ch = 0; ch < 4; ++ch) {
-                uint32_t r[32];
-                tmem_ld_32x32b_x32(tS + ch * 32, r);
+            if (!masked) {
+                uint32_t ra[32], rb[32];
+                tmem_ld_32x32b_x32(tS, ra);
                 tmem_ld_wait();
-                mx = masked ? row_max_chunk<true>(r, ch * 32, valid, mx) : row_max_chunk<false>(r, ch * 32, valid, mx);
+                tmem_ld_32x32b_x32(tS + 32, rb);
+                mx = row_max_chunk(ra, mx);
+                tmem_ld_wait();
+                tmem_ld_32x32b_x32(tS + 64, ra);
+                mx = row_max_chunk(rb, mx);
+                tmem_ld_wait();
+                tmem_ld_32x32b_x32(tS + 96, rb);
+                mx = row_max_chunk(ra, mx);
+                tmem_ld_wait();
+                mx = row_max_chunk(rb, mx);
+            } else {                                             // ragged last KV tile (S % 128 != 0): simple rolled loop
+#pragma unroll 1
+                for (int ch = 0; ch < 4; ++ch) {
+                    uint32_t r[32];
+                    tmem_ld_32x32b_x32(tS + ch * 32, r);
+                    tmem_ld_wait();
+                    mask_chunk(r, ch * 32, valid);
+                    mx = row_max_chunk(r, mx);
+                }
             }
             float alpha = 1.f;
             const bool grow = (mx - m_ref) * c > kRescaleThreshold;
@@ -238,7 +253,6 @@ attn_spatial_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
                 const float m_new = fmaxf(m_ref, mx);
                 alpha = (m_ref == -INFINITY) ? 0.f : fast_exp2((m_ref - m_new) * c);
                 m_ref = m_new;
-                l *= alpha;
             }
             if (j > 0) {
                 // the P_t buffer and O_t belong to the tensor core until PV of tile j-1 has retired
@@ -246,7 +260,7 @@ attn_spatial_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
                 tc_fence_after();
                 if (any_grow) {
 #pragma unroll
-                    for (int ch = 0; ch < 4; ++ch) {
+                    for (int ch = 0; ch < kOCols / 16; ++ch) {      // 64 output columns + the row-sum columns
                         uint32_t r[16];
                         tmem_ld_32x32b_x16(tO + ch * 16, r);
                         tmem_ld_wait();
@@ -259,17 +273,35 @@ attn_spatial_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
             }
             // pass 2: p = 2^((s - m_ref) * c) in packed fp16 -> P smem (K-major, SWIZZLE_128B, two 64-key halves)
             const float mc = m_ref * c;
-#pragma unroll
-            for (int ch = 0; ch < 4; ++ch) {
-                uint32_t r[32];
-                tmem_ld_32x32b_x32(tS + ch * 32, r);
+            if (!masked) {
+                uint32_t ra[32], rb[32];
+                tmem_ld_32x32b_x32(tS, ra);
                 tmem_ld_wait();
-                if (ch == 3) {                                   // last read of S_t: release it for the next QK
-                    tc_fence_before();
-                    mbar_arrive(bar_s_free + 8 * t);
+                tmem_ld_32x32b_x32(tS + 32, rb);
+                exp_chunk(ra, 0, c, mc, pP, sw);
+                tmem_ld_wait();
+                tmem_ld_32x32b_x32(tS + 64, ra);
+                exp_chunk(rb, 1, c, mc, pP, sw);
+                tmem_ld_wait();
+                tmem_ld_32x32b_x32(tS + 96, rb);
+                exp_chunk(ra, 2, c, mc, pP + kTileBytes, sw);
+                tmem_ld_wait();
+                tc_fence_before();                               // last read of S_t: release it for the next QK
+                mbar_arrive(bar_s_free + 8 * t);
+                exp_chunk(rb, 3, c, mc, pP + kTileBytes, sw);
+            } else {
+#pragma unroll 1
+                for (int ch = 0; ch < 4; ++ch) {
+                    uint32_t r[32];
+                    tmem_ld_32x32b_x32(tS + ch * 32, r);
+                    tmem_ld_wait();
+                    if (ch == 3) {
+                        tc_fence_before();
+                        mbar_arrive(bar_s_free + 8 * t);
+                    }
+                    mask_chunk(r, ch * 32, valid);
+                    exp_chunk(r, ch, c, mc, pP + (ch >> 1) * kTileBytes, sw);
                 }
-                uint8_t* dst = pP + (ch >> 1) * kTileBytes;
-                l += masked ? exp_chunk<true>(r, ch, valid, c, mc, dst, sw) : exp_chunk<false>(r, ch, valid, c, mc, dst, sw);
             }
             fence_proxy_async_smem();
             tc_fence_before();
@@ -278,7 +310,13 @@ attn_spatial_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
         // ---- epilogue: O / l -> fp16 -> smem (SW128, first half of this tile's P buffer) -> TMA store
         mbar_wait(bar_pv_done + 8 * t, (uint32_t)(nkv - 1) & 1u);
         tc_fence_after();
-        const float inv = 1.f / l;
+        float inv;
+        {
+            uint32_t r[16];
+            tmem_ld_32x32b_x16(tO + 64, r);                      // row sum l = (P @ ones), fp32 from the tensor core
+            tmem_ld_wait();
+            inv = 1.f / __uint_as_float(r[0]);
+        }
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch) {
             uint32_t r[16];

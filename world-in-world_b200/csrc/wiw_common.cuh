@@ -71,9 +71,12 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 }
 // Spin on the phase parity.  A kernel that waits ~2 s has a protocol bug: trap instead of
 // hanging the device.
+static __device__ __noinline__ void mbar_timeout_trap(uint32_t bar) {
+    printf("wiw: mbarrier timeout (block %d thread %d bar 0x%x)\n", blockIdx.x, threadIdx.x, bar);
+    __trap();
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t done = 0;
-    long long t0 = 0;
     uint32_t spins = 0;
     while (true) {
         asm volatile(
@@ -84,11 +87,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             : "r"(bar), "r"(parity)
             : "memory");
         if (done) break;
-        if ((++spins & 0xfff) == 0) {
-            long long now = clock64();
-            if (t0 == 0) t0 = now;
-            else if (now - t0 > 4000000000LL) { printf("wiw: mbarrier timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x); __trap(); }
-        }
+        if (++spins > (1u << 24)) mbar_timeout_trap(bar);      // seconds of failed try_waits: protocol bug
     }
 }
 
