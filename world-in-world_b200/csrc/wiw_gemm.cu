@@ -227,21 +227,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 tc_fence_before();
                 mbar_arrive(bar_tempty + 8 * as);
             }
-            // raw accumulator chunk(s) of this group are prefetched from TMEM one chunk ahead, so the load latency
-            // hides behind the previous chunk's staging / barrier / TMA-store phase
-            uint32_t rv[kEpiCols], rg[kEpiCols];
-            const int half_n = g.bn >> 1;
-            if (last_j >= 0) {
-                tmem_ld_32x32b_x32(t_acc + grp * kEpiCols, rv);
-                if (g.geglu) tmem_ld_32x32b_x32(t_acc + half_n + grp * kEpiCols, rg);
-            }
             for (int j = grp; j < chunks; j += 2) {
                 float v[kEpiCols];
-                tmem_ld_wait();
                 {
+                    uint32_t r[kEpiCols];
+                    tmem_ld_32x32b_x32(t_acc + j * kEpiCols, r);
+                    tmem_ld_wait();
                     const int nb = acc_n0 + j * kEpiCols;
 #pragma unroll
-                    for (int c = 0; c < kEpiCols; ++c) v[c] = __uint_as_float(rv[c]);
+                    for (int c = 0; c < kEpiCols; ++c) v[c] = __uint_as_float(r[c]);
                     if (g.bias != nullptr) {
 #pragma unroll
                         for (int c = 0; c < kEpiCols; c += 4) {
@@ -267,23 +261,24 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                     }
                 }
                 if (g.geglu) {
+                    uint32_t r[kEpiCols];
+                    const int half_n = g.bn >> 1;
+                    tmem_ld_32x32b_x32(t_acc + half_n + j * kEpiCols, r);
+                    tmem_ld_wait();
                     const int nb = acc_n0 + half_n + j * kEpiCols;
 #pragma unroll
                     for (int c = 0; c < kEpiCols; c += 4) {
                         const float4 b4 = (g.bias != nullptr) ? __ldg(reinterpret_cast<const float4*>(g.bias + nb + c)) : make_float4(0, 0, 0, 0);
-                        v[c] *= gelu_fast_f(__uint_as_float(rg[c]) + b4.x);
-                        v[c + 1] *= gelu_fast_f(__uint_as_float(rg[c + 1]) + b4.y);
-                        v[c + 2] *= gelu_fast_f(__uint_as_float(rg[c + 2]) + b4.z);
-                        v[c + 3] *= gelu_fast_f(__uint_as_float(rg[c + 3]) + b4.w);
+                        v[c] *= gelu_fast_f(__uint_as_float(r[c]) + b4.x);
+                        v[c + 1] *= gelu_fast_f(__uint_as_float(r[c + 1]) + b4.y);
+                        v[c + 2] *= gelu_fast_f(__uint_as_float(r[c + 2]) + b4.z);
+                        v[c + 3] *= gelu_fast_f(__uint_as_float(r[c + 3]) + b4.w);
                     }
                 }
                 if (j == last_j) {
                     // this group's TMEM reads of the accumulator stage are done: hand it back to the MMA warp
                     tc_fence_before();
                     mbar_arrive(bar_tempty + 8 * as);
-                } else {
-                    tmem_ld_32x32b_x32(t_acc + (j + 2) * kEpiCols, rv);
-                    if (g.geglu) tmem_ld_32x32b_x32(t_acc + half_n + (j + 2) * kEpiCols, rg);
                 }
                 if (g.s_acc != 1.0f) {
 #pragma unroll

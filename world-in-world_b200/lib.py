@@ -13,7 +13,8 @@ from typing import Optional
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libwiw_b200.so")
+# WIW_B200_LIB lets perf scripts A/B an alternative build of the SAME library (development aid, not a fallback)
+LIB_PATH = os.environ.get("WIW_B200_LIB", os.path.join(_HERE, "libwiw_b200.so"))
 ABI_VERSION = 1
 
 
