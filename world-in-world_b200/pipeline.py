@@ -37,8 +37,9 @@ def sample_latent_noise_(noise: torch.Tensor, actions: torch.Tensor) -> torch.Te
 
 
 class Rollout:
-    def __init__(self, unet: UNetEngine, vae: Optional[VAEDecoderEngine], device="cuda"):
+    def __init__(self, unet: UNetEngine, vae: Optional[VAEDecoderEngine], device="cuda", use_cuda_graph: bool = True):
         self.unet, self.vae = unet, vae
+        self.use_cuda_graph = use_cuda_graph
         self.device = torch.device(device)
         self.F = unet.cfg.num_frames
         self._sched_cache = {}
@@ -72,7 +73,7 @@ class Rollout:
         st = L.stream_ptr
         for i, sc in enumerate(steps):
             L.check(lib.wiw_sampler_prepare(lat.data_ptr(), img.data_ptr(), x_in.data_ptr(), F, hw, sc.div, st()))
-            v = self.unet.forward(x_in, t_embs[i:i + 1])
+            v = (self.unet.forward_graphed if self.use_cuda_graph else self.unet.forward)(x_in, t_embs[i:i + 1])
             L.check(lib.wiw_sampler_step(v.data_ptr(), lat.data_ptr(), gs.data_ptr(), F, hw, v.shape[-1], sc.c_out,
                                          sc.sig2p1, sc.sigma, sc.dt, st()))
             if trace is not None:
