@@ -16,6 +16,8 @@
 #include "wiw_common.cuh"
 #include "../../include/wiw.h"
 
+#include <cstdlib>
+
 namespace wiw {
 
 constexpr int kBlockM = 128;
@@ -29,7 +31,7 @@ constexpr int kThreads = 11 * 32;              // TMA, MMA, epilogue loader, 2 x
 constexpr int kSmemBudget = 227 * 1024;
 
 struct GemmArgs {
-    int total_tiles, n_tiles, tiles_x, tiles_y;
+    int total_tiles, n_tiles, tiles_x, tiles_y;   // total_tiles counts PAIR tiles when cta_group == 2
     int bx, by, dim_x, dim_y;
     int bn, stages, num_taps, chunks_per_tap;
     int out_cols_per_tile, geglu, has_res, has_aux;
@@ -44,10 +46,14 @@ struct GemmArgs {
 struct TileCoord {
     int x0, y0, img, n_tile;
 };
-__device__ __forceinline__ TileCoord decode_tile(const GemmArgs& g, int tile) {
+// tile = index of a (pair of) M-tile(s) x N-tile; with cta_group::2 CTA `rank` of the pair owns M-tile 2*mp + rank
+// (an M-tile past the end decodes to an out-of-range image: its loads zero-fill and its stores clip)
+template <int CG>
+__device__ __forceinline__ TileCoord decode_tile(const GemmArgs& g, int tile, int rank) {
     TileCoord t;
-    int m_tile = tile / g.n_tiles;
-    t.n_tile = tile - m_tile * g.n_tiles;
+    const int mp = tile / g.n_tiles;
+    t.n_tile = tile - mp * g.n_tiles;
+    const int m_tile = mp * CG + rank;
     int tx = m_tile % g.tiles_x;
     int r = m_tile / g.tiles_x;
     int ty = r % g.tiles_y;
@@ -57,6 +63,7 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmArgs& g, int tile) {
     return t;
 }
 
+template <int CG>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                  const __grid_constant__ CUtensorMap tm_out, const __grid_constant__ CUtensorMap tm_res,
@@ -65,7 +72,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     // carve: [stages x (A 16 KB | B bn*128)] [out bufs] [res slots] [aux slots] [barriers]
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t a_bytes = kBlockM * kBlockK * 2;
-    const uint32_t b_bytes = g.bn * kBlockK * 2;
+    const uint32_t b_bytes = (g.bn / CG) * kBlockK * 2;          // with cta_group::2 each CTA stages half of the N-tile
     const uint32_t stage_bytes = a_bytes + b_bytes;
     const uint32_t out_base = smem_base + g.stages * stage_bytes;
     const uint32_t res_base = out_base + kOutBufs * kEpiChunkBytes;
@@ -85,6 +92,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     const int lane = threadIdx.x & 31;
     const int k_iters = g.num_taps * g.chunks_per_tap;
     const bool has_epi_loads = g.has_res || g.has_aux;
+    const int cta_rank = (CG == 2) ? (int)cluster_ctarank() : 0;
+    const int first_tile = blockIdx.x / CG, tile_step = gridDim.x / CG;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tm_a);
@@ -100,7 +109,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(bar_tfull + 8 * i, 1);
-            mbar_init(bar_tempty + 8 * i, 256);
+            mbar_init(bar_tempty + 8 * i, 8 * CG);       // one arrival per epilogue warp of every CTA in the pair
         }
         for (int i = 0; i < kResSlots; ++i) {
             mbar_init(bar_rfull + 8 * i, 1);
@@ -109,11 +118,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         fence_barrier_init();
     }
     if (warp == 2) {
-        tmem_alloc(tmem_slot, g.tmem_cols);
-        tmem_relinquish();
+        if (CG == 2) { tmem_alloc_2sm(tmem_slot, g.tmem_cols); tmem_relinquish_2sm(); }
+        else { tmem_alloc(tmem_slot, g.tmem_cols); tmem_relinquish(); }
     }
     tc_fence_before();
-    __syncthreads();
+    if (CG == 2) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
     const uint32_t acc_stride = (g.bn <= 32) ? 32 : (g.bn <= 64 ? 64 : (g.bn <= 128 ? 128 : 256));
@@ -123,18 +132,25 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         if (lane == 0) {
             int s = 0;
             uint32_t ph = 0;
-            for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
-                const TileCoord t = decode_tile(g, tile);
-                const int n0 = t.n_tile * g.bn;
+            for (int tile = first_tile; tile < g.total_tiles; tile += tile_step) {
+                const TileCoord t = decode_tile<CG>(g, tile, cta_rank);
+                const int n0 = t.n_tile * g.bn + cta_rank * (g.bn / CG);
                 int kcol = 0;
                 for (int tap = 0; tap < g.num_taps; ++tap) {
                     const int cb = g.tap_cbase[tap], cx = t.x0 + g.tap_ox[tap], cp = g.tap_p[tap], cy = t.y0 + g.tap_oy[tap];
                     for (int ch = 0; ch < g.chunks_per_tap; ++ch) {
                         mbar_wait(bar_empty + 8 * s, ph ^ 1);
                         const uint32_t sa = smem_base + s * stage_bytes;
-                        mbar_expect_tx(bar_full + 8 * s, stage_bytes);
-                        tma_load_5d(sa, &tm_a, bar_full + 8 * s, cb + ch * kBlockK, cx, cp, cy, t.img);
-                        tma_load_2d(sa + a_bytes, &tm_b, bar_full + 8 * s, kcol, n0);
+                        if (CG == 2) {
+                            // both CTAs' bytes are credited to the leader's barrier; only the leader arms it
+                            if (cta_rank == 0) mbar_expect_tx(bar_full + 8 * s, 2 * stage_bytes);
+                            tma_load_5d_2sm(sa, &tm_a, bar_full + 8 * s, cb + ch * kBlockK, cx, cp, cy, t.img);
+                            tma_load_2d_2sm(sa + a_bytes, &tm_b, bar_full + 8 * s, kcol, n0);
+                        } else {
+                            mbar_expect_tx(bar_full + 8 * s, stage_bytes);
+                            tma_load_5d(sa, &tm_a, bar_full + 8 * s, cb + ch * kBlockK, cx, cp, cy, t.img);
+                            tma_load_2d(sa + a_bytes, &tm_b, bar_full + 8 * s, kcol, n0);
+                        }
                         kcol += kBlockK;
                         if (++s == g.stages) { s = 0; ph ^= 1; }
                     }
@@ -143,13 +159,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         }
     } else if (warp == 1) {
         // ================================ MMA issuer ================================
-        if (lane == 0) {
-            const uint32_t idesc = make_idesc_f16(g.bn);
+        if (lane == 0 && cta_rank == 0) {                 // the leader CTA issues the MMAs of the pair
+            const uint32_t idesc = make_idesc_f16(g.bn, 0, 0, 128 * CG);
             int s = 0;
             uint32_t ph = 0;
             int as = 0;
             uint32_t aph = 0;
-            for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
+            for (int tile = first_tile; tile < g.total_tiles; tile += tile_step) {
                 mbar_wait(bar_tempty + 8 * as, aph ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + as * acc_stride;
@@ -162,12 +178,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 #pragma unroll
                     for (int kk = 0; kk < kBlockK / 16; ++kk) {
                         // +32 bytes per K=16 step inside the 128-byte swizzle row (units of 16 B)
-                        umma_f16_ss(d_tmem, da + 2 * kk, db + 2 * kk, idesc, (it > 0 || kk > 0) ? 1u : 0u);
+                        if (CG == 2) umma_f16_ss_2sm(d_tmem, da + 2 * kk, db + 2 * kk, idesc, (it > 0 || kk > 0) ? 1u : 0u);
+                        else umma_f16_ss(d_tmem, da + 2 * kk, db + 2 * kk, idesc, (it > 0 || kk > 0) ? 1u : 0u);
                     }
-                    umma_commit(bar_empty + 8 * s);          // frees the smem stage when the MMAs retire
+                    // frees the smem stage (in both CTAs of a pair) when the MMAs retire
+                    if (CG == 2) umma_commit_2sm(bar_empty + 8 * s, 3); else umma_commit(bar_empty + 8 * s);
                     if (++s == g.stages) { s = 0; ph ^= 1; }
                 }
-                umma_commit(bar_tfull + 8 * as);             // accumulator ready for the epilogue
+                if (CG == 2) umma_commit_2sm(bar_tfull + 8 * as, 3); else umma_commit(bar_tfull + 8 * as);   // accumulator ready
                 if (++as == 2) { as = 0; aph ^= 1; }
             }
         }
@@ -178,8 +196,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             const uint32_t bytes = kEpiChunkBytes * ((g.has_res ? 1 : 0) + (g.has_aux ? 1 : 0));
             int rs = 0;
             uint32_t rph = 0;
-            for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
-                const TileCoord t = decode_tile(g, tile);
+            for (int tile = first_tile; tile < g.total_tiles; tile += tile_step) {
+                const TileCoord t = decode_tile<CG>(g, tile, cta_rank);
                 const int c0 = t.n_tile * g.out_cols_per_tile;
                 for (int j = 0; j < chunks; ++j) {
                     mbar_wait(bar_rempty + 8 * rs, rph ^ 1);
@@ -207,8 +225,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         uint32_t aph = 0;
         int ob = 0;                                    // this group's staging buffer (2 per group)
         long long chunk_base = 0;                      // chunks consumed by this CTA before the current tile
-        for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, chunk_base += chunks) {
-            const TileCoord t = decode_tile(g, tile);
+        for (int tile = first_tile; tile < g.total_tiles; tile += tile_step, chunk_base += chunks) {
+            const TileCoord t = decode_tile<CG>(g, tile, cta_rank);
             const int acc_n0 = t.n_tile * g.bn;                       // first GEMM column of this tile
             const int out_c0 = t.n_tile * g.out_cols_per_tile;        // first output channel
             const __half* tab_row = nullptr;
@@ -225,7 +243,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             const int last_j = ((chunks - 1 - grp) >= 0) ? (grp + 2 * ((chunks - 1 - grp) / 2)) : -1;
             if (last_j < 0) {                          // nothing to do for this group in this tile
                 tc_fence_before();
-                mbar_arrive(bar_tempty + 8 * as);
+                __syncwarp();
+                if (lane == 0) { if (CG == 2) mbar_arrive_cluster(bar_tempty + 8 * as, 0); else mbar_arrive(bar_tempty + 8 * as); }
             }
             for (int j = grp; j < chunks; j += 2) {
                 float v[kEpiCols];
@@ -278,7 +297,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 if (j == last_j) {
                     // this group's TMEM reads of the accumulator stage are done: hand it back to the MMA warp
                     tc_fence_before();
-                    mbar_arrive(bar_tempty + 8 * as);
+                    __syncwarp();
+                    if (lane == 0) { if (CG == 2) mbar_arrive_cluster(bar_tempty + 8 * as, 0); else mbar_arrive(bar_tempty + 8 * as); }
                 }
                 if (g.s_acc != 1.0f) {
 #pragma unroll
@@ -349,9 +369,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     }
 
     tc_fence_before();
-    __syncthreads();
+    if (CG == 2) cluster_sync_all(); else __syncthreads();      // the peer may still read this CTA's smem / signal its barriers
     if (warp == 2) {
         tc_fence_after();
+        if (CG == 2) tmem_dealloc_2sm(tmem_base, g.tmem_cols); else
         tmem_dealloc(tmem_base, g.tmem_cols);
     }
 }
@@ -383,7 +404,16 @@ static int launch_conv_gemm(const wiw_gemm_desc* d, cudaStream_t stream) {
     g.n_tiles = (int)(d->n_total / d->bn);
     const long long m_tiles = (long long)g.tiles_x * g.tiles_y * d->out_dim[3];
     WIW_REQUIRE(m_tiles * g.n_tiles < (1LL << 31), "too many tiles");
-    g.total_tiles = (int)(m_tiles * g.n_tiles);
+    // CTA pairs (cta_group::2, M = 256 per MMA, each CTA stages half of the weight tile) whenever the problem
+    // fills the machine; small problems keep single-CTA tiles
+    static const int force_cg = getenv("WIW_GEMM_CG") ? atoi(getenv("WIW_GEMM_CG")) : 0;      // development aid for A/B runs
+    // Measured on B200 (profiles/r01_gemm_pair_ab.md): pairs win when the reduction is long enough to amortise the
+    // cross-CTA handshakes -- plain GEMMs with K >= 1280, N-tile-256 problems with K >= 640, convs with >= 960 input
+    // channels -- and lose a few % on the short-K projections and the 320/640-channel convs.
+    const bool pair_shape = (d->k_total >= 1280) && (d->num_taps == 1 || d->bn == 256 || d->chunks_per_tap >= 15);
+    int cg = (pair_shape && m_tiles * g.n_tiles >= 2LL * num_sms()) ? 2 : 1;
+    if (force_cg == 1 || force_cg == 2) cg = force_cg;
+    g.total_tiles = (int)(((m_tiles + cg - 1) / cg) * g.n_tiles);
     g.bn = d->bn;
     g.num_taps = d->num_taps; g.chunks_per_tap = d->chunks_per_tap;
     g.geglu = d->geglu ? 1 : 0;
@@ -398,8 +428,9 @@ static int launch_conv_gemm(const wiw_gemm_desc* d, cudaStream_t stream) {
     }
     int cols = 2 * ((g.bn <= 32) ? 32 : (g.bn <= 64 ? 64 : (g.bn <= 128 ? 128 : 256)));
     g.tmem_cols = cols;       // power of two in [64, 512]
+    if (cg == 2) g.tmem_cols = 512;   // pair allocations always take the whole TMEM (as CUTLASS does): both CTAs must see the same base
 
-    const int stage_bytes = kBlockM * kBlockK * 2 + g.bn * kBlockK * 2;
+    const int stage_bytes = kBlockM * kBlockK * 2 + (g.bn / cg) * kBlockK * 2;
     const int fixed = 1024 /*align slack*/ + kOutBufs * kEpiChunkBytes + (g.has_res ? kResSlots * kEpiChunkBytes : 0) +
                       (g.has_aux ? kResSlots * kEpiChunkBytes : 0) + 256 /*barriers*/;
     int stages = (kSmemBudget - fixed) / stage_bytes;
@@ -420,7 +451,7 @@ static int launch_conv_gemm(const wiw_gemm_desc* d, cudaStream_t stream) {
     {
         uint64_t dims[2] = {(uint64_t)d->k_total, (uint64_t)d->n_total};
         uint64_t strides[1] = {(uint64_t)d->k_total * 2};
-        uint32_t box[2] = {(uint32_t)kBlockK, (uint32_t)d->bn};
+        uint32_t box[2] = {(uint32_t)kBlockK, (uint32_t)(d->bn / cg)};
         if (encode_tmap(&tm_b, d->w, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return 3;
     }
     auto enc_out = [&](CUtensorMap* m, const void* p, const int64_t* st) -> int {
@@ -436,12 +467,30 @@ static int launch_conv_gemm(const wiw_gemm_desc* d, cudaStream_t stream) {
 
     static bool attr_set = false;
     if (!attr_set) {
-        WIW_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+        WIW_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+        WIW_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
         attr_set = true;
     }
-    int grid = num_sms();
-    if (grid > g.total_tiles) grid = g.total_tiles;
-    conv_gemm_kernel<<<grid, kThreads, smem_bytes, stream>>>(tm_a, tm_b, tm_out, tm_res, tm_aux, g);
+    if (cg == 1) {
+        int grid = num_sms();
+        if (grid > g.total_tiles) grid = g.total_tiles;
+        conv_gemm_kernel<1><<<grid, kThreads, smem_bytes, stream>>>(tm_a, tm_b, tm_out, tm_res, tm_aux, g);
+    } else {
+        int pairs = num_sms() / 2;
+        if (pairs > g.total_tiles) pairs = g.total_tiles;
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(2 * pairs);
+        cfg.blockDim = dim3(kThreads);
+        cfg.dynamicSmemBytes = smem_bytes;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        WIW_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<2>, tm_a, tm_b, tm_out, tm_res, tm_aux, g));
+    }
     WIW_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
