@@ -30,13 +30,15 @@ __device__ __forceinline__ void acc8(const uint4& u, float* s, float* q) {
 // grid (chunks, samples); block = vpr * RL threads, thread (v, rl) owns channels [8v, 8v+8) and rows rl, rl+RL, ...
 __global__ void gn_stats_kernel(const __half* __restrict__ x, float* __restrict__ partial, long long rows_per_sample,
                                 int C, int G, int rows_per_chunk, int vpr, int RL) {
-    extern __shared__ float sm[];            // [2*C]
-    float* s_sum = sm;
-    float* s_sq = sm + C;
+    // smem: per-row-lane partials [RL][C] for sum and sumsq, then [C] column totals; fixed summation order
+    // (no atomics) so the statistics -- and the whole rollout -- are bit-reproducible run to run
+    extern __shared__ float sm[];
+    float* p_sum = sm;                       // [RL][C]
+    float* p_sq = sm + (size_t)RL * C;       // [RL][C]
+    float* s_sum = p_sq + (size_t)RL * C;    // [C]
+    float* s_sq = s_sum + C;                 // [C]
     const int chunk = blockIdx.x, n = blockIdx.y;
     const int v = threadIdx.x % vpr, rl = threadIdx.x / vpr;
-    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sm[i] = 0.f;
-    __syncthreads();
     float s[8], q[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) { s[e] = 0.f; q[e] = 0.f; }
@@ -59,8 +61,14 @@ __global__ void gn_stats_kernel(const __half* __restrict__ x, float* __restrict_
     }
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-        atomicAdd(&s_sum[v * 8 + e], s[e]);
-        atomicAdd(&s_sq[v * 8 + e], q[e]);
+        p_sum[rl * C + v * 8 + e] = s[e];
+        p_sq[rl * C + v * 8 + e] = q[e];
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float a = 0.f, b = 0.f;
+        for (int k = 0; k < RL; ++k) { a += p_sum[k * C + c]; b += p_sq[k * C + c]; }
+        s_sum[c] = a; s_sq[c] = b;
     }
     __syncthreads();
     const int cg = C / G;
@@ -267,7 +275,7 @@ extern "C" int wiw_groupnorm(const void* x, void* y, int samples, long long rows
     const int chunks = (int)((rows_per_sample + rpc - 1) / rpc);
     float* partial = workspace;
     float* stats = workspace + (size_t)samples * kGnMaxChunks * G * 2;
-    gn_stats_kernel<<<dim3(chunks, samples), threads, 2 * C * sizeof(float), stream>>>(
+    gn_stats_kernel<<<dim3(chunks, samples), threads, (size_t)(2 * RL + 2) * C * sizeof(float), stream>>>(
         static_cast<const __half*>(x), partial, rows_per_sample, C, G, (int)rpc, vpr, RL);
     WIW_CHECK_CUDA(cudaGetLastError());
     const int warps = samples * G;
