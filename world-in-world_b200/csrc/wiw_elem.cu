@@ -387,8 +387,11 @@ static int launch_tattn(const void* qkv, void* out, int B, int S, int C, cudaStr
     return 0;
 }
 
+extern "C" int wiw_attention_temporal_mma(const void* qkv, void* out, int B, int F, int S, int C, void* stream);   // wiw_tattn.cu
+
 extern "C" int wiw_attention_temporal(const void* qkv, void* out, int B, int F, int S, int C, wiw_stream_t st) {
     WIW_REQUIRE(qkv && out && C % 64 == 0, "bad args");
+    if (F <= 16) return wiw_attention_temporal_mma(qkv, out, B, F, S, C, st);     // warp-level tensor-core kernel
     switch (F) {
         case 2: return launch_tattn<2>(qkv, out, B, S, C, STREAM(st));
         case 4: return launch_tattn<4>(qkv, out, B, S, C, STREAM(st));
