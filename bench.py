@@ -287,8 +287,9 @@ def main():
         if world > 1:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         e2e = {"value": world * F * reps / float(dt.item()), "unit": "frames/s", "h2d_bytes_per_step": int(b_image.nbytes + acts.nbytes),
-               "d2h_bytes_per_step": int(F * 3 * H * W), "api": "wm_worker.WorldModelWorker.do_some_tasks (request dict -> pred_frames uint8)",
-               "includes": "CLIP ViT-H + fp32 VAE encode (PyTorch), 25-step rollout, decode, D2H of 576x1024 frames, PIL bicubic 480x480"}
+               "d2h_bytes_per_step": int(out["pred_frames"].nbytes), "api": "wm_worker.WorldModelWorker.do_some_tasks (request dict -> pred_frames uint8)",
+               "includes": "H2D of the uint8 observation, CLIP ViT-H + fp32 VAE encode (PyTorch), 25-step rollout, decode, "
+                           "Pillow-exact bicubic 480x480 + requantisation on the GPU, D2H of the uint8 frames"}
 
     cpu_b = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -141,6 +141,13 @@ int wiw_frames_to_u8(const void* x, void* out, long long F, long long HW, int cs
  * x fp16 [F][HW][cs]; w fp32 [3][3][3] (co,ci,kt); out_u8 [F][3][HW] and/or out_f32 [F][3][HW] (pre-quantisation). */
 int wiw_vae_finish(const void* x, const float* w, const float* bias, void* out_u8, float* out_f32, int F,
                    long long HW, int cs, wiw_stream_t stream);
+/* Pillow-exact BICUBIC resize of uint8 planes [planes][H][W] -> [planes][oh][ow] (22-bit fixed-point two-pass resampler,
+ * 8-bit intermediate in `tmp` [planes][H][ow]) followed by a 256-entry requantisation LUT: replaces the CPU
+ * `img.resize(save_size, Image.BICUBIC)` + to_tensor + (clip*255).astype(uint8) of downstream/api_models/__init__.py:159-166,229.
+ * bounds_* int32 [out][2] = (first source index, taps), kk_* int32 [out][ksize] built by wiw_b200/resize.py. */
+int wiw_resize_bicubic_u8(const void* src, void* tmp, void* dst, long long planes, int H, int W, int oh, int ow,
+                          const int* bounds_h, const int* kk_h, int ksize_h, const int* bounds_v, const int* kk_v, int ksize_v,
+                          const void* lut, wiw_stream_t stream);
 /* Boundary layout converters: fp16 [N][C][P] <-> channels-last [N][P][cs] (cs >= C, padding zero). */
 int wiw_nchw_to_nhwc(const void* src, void* dst, long long N, int C, long long P, int cs, wiw_stream_t stream);
 int wiw_nhwc_to_nchw(const void* src, void* dst, long long N, int C, long long P, int cs, wiw_stream_t stream);

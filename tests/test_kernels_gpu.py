@@ -160,3 +160,19 @@ def test_vae_finish_and_u8():
     close(f32, ref, "time_conv_out")
     q = ((f32 / 2 + 0.5).clamp(0, 1) * 255).round().to(torch.uint8)
     assert torch.equal(u8, q)
+
+
+@pytest.mark.parametrize("H,W,oh,ow", [(576, 1024, 480, 480), (64, 128, 40, 48), (30, 40, 50, 64)])
+def test_gpu_resize_is_pil_exact(H, W, oh, ow):
+    """wiw_resize_bicubic_u8 == PIL Image.resize(BICUBIC) byte for byte, then the reference's requantisation chain."""
+    from PIL import Image
+    from wiw_b200.resize import GpuResizer
+    rng = np.random.default_rng(H + W)
+    planes = rng.integers(0, 256, size=(2, 3, H, W), dtype=np.uint8)
+    out = GpuResizer(H, W, oh, ow, DEV, requant=False)(torch.from_numpy(planes).to(DEV)).cpu().numpy()
+    for i in range(2):
+        ref = np.asarray(Image.fromarray(planes[i].transpose(1, 2, 0)).resize((ow, oh), Image.BICUBIC)).transpose(2, 0, 1)
+        assert np.array_equal(out[i], ref)
+    out2 = GpuResizer(H, W, oh, ow, DEV, requant=True)(torch.from_numpy(planes).to(DEV)).cpu().numpy()
+    f = out.astype(np.float32) / np.float32(255)
+    assert np.array_equal(out2, (np.clip(f, 0, 1) * 255).astype(np.uint8))

@@ -187,7 +187,7 @@ class Navigator:
 
     @torch.no_grad()
     def inference(self, actions: torch.Tensor, images_u8: np.ndarray, out_width=None, out_height=None,
-                  latents: Optional[torch.Tensor] = None) -> np.ndarray:
+                  latents: Optional[torch.Tensor] = None, on_device: bool = False):
         """actions int64/float [b, F, F] (action_ids_idx_encode); images_u8 uint8 [b, 3, H, W].
         Returns uint8 frames [b, F, 3, H, W] (the pipeline's PIL frames).  Branches run one after another
         (request batch 1 per UNet call, as the reference deployment does)."""
@@ -198,7 +198,7 @@ class Navigator:
         b = actions.shape[0]
         F, H, W = self.num_frames, self.image_height, self.image_width
         sched = EulerSchedule(self.num_inference_steps)
-        out = np.empty((b, F, 3, H, W), dtype=np.uint8)
+        out = torch.empty((b, F, 3, H, W), dtype=torch.uint8, device=dev)
         img = torch.from_numpy(images_u8[:, :3]).to(dev).float() / 255.0                    # pil_to_numpy/numpy_to_pt: [0,1]
         if img.shape[-2:] != (H, W):
             img = torch.nn.functional.interpolate(img, size=(H, W), mode="bilinear", antialias=True)
@@ -217,8 +217,8 @@ class Navigator:
         for i in range(b):
             lat = self.rollout.denoise(raw[i], image_latents[i], emb[i], actions[i].float(), num_steps=self.num_inference_steps,
                                        noise_aug_strength=self.noise_aug_strength)
-            out[i] = self.rollout.decode(lat).cpu().numpy()
-        return out
+            out[i] = self.rollout.decode(lat)
+        return out if on_device else out.cpu().numpy()
 
 
 class WorldModelWorker:
@@ -243,10 +243,16 @@ class WorldModelWorker:
             assert b_image.ndim == 4 and b_image.dtype == np.uint8, f"b_image should be uint8 B C H W, got {b_image.shape}"
             assert len(b_action) == len(save_dirs)
             action_ids = action_ids_idx_encode(b_action)
-            frames = self.nav.inference(action_ids, b_image, self.args.out_width, self.args.out_height)
-            video = images_to_tensor(frames, save_size=(self.args.out_width, self.args.out_height)).numpy()
+            frames = self.nav.inference(action_ids, b_image, self.args.out_width, self.args.out_height, on_device=True)
             if return_objects:
-                return {"pred_frames": (np.clip(video, 0, 1) * 255).astype(np.uint8), "save_dirs": save_dirs}
+                # PIL BICUBIC resize + the reference's double quantisation, byte-exact, on the GPU (wiw_resize_bicubic_u8):
+                # only the 480x480 uint8 result crosses PCIe
+                key = (frames.shape[-2], frames.shape[-1], self.args.out_height, self.args.out_width)
+                if getattr(self, "_resizer_key", None) != key:
+                    from .resize import GpuResizer
+                    self._resizer, self._resizer_key = GpuResizer(*key, device=frames.device), key
+                return {"pred_frames": self._resizer(frames).cpu().numpy(), "save_dirs": save_dirs}
+            video = images_to_tensor(frames.cpu().numpy(), save_size=(self.args.out_width, self.args.out_height)).numpy()
             save_predict(video, b_action, save_dirs)
             return {"save_dirs": save_dirs}
         except Exception:                       # never die inside task_fn (SURVEY.md 8b "Errors")
