@@ -28,7 +28,8 @@ def close(y: torch.Tensor, ref: torch.Tensor, what=""):
     assert bad == 0, f"{what}: {bad} elements out of tolerance, max err {err.max().item():.4g} (scale {scale:.3g})"
 
 
-@pytest.mark.parametrize("m,k,n", [(300, 128, 160), (128, 64, 32), (4032, 320, 960), (1000, 1280, 320), (17, 64, 256)])
+@pytest.mark.parametrize("m,k,n", [(300, 128, 160), (128, 64, 32), (4032, 320, 960), (1000, 1280, 320), (17, 64, 256),
+                                   (700, 192, 640), (260, 64, 288), (40000, 1280, 640)])   # last three: ragged last N-tile (bn 224 / 160)
 def test_linear_bias(m, k, n):
     x = rnd(m, k, seed=1).half().to(DEV)
     w, b = rnd(n, k, seed=2, scale=k ** -0.5), rnd(n, seed=3)
@@ -78,7 +79,7 @@ def test_geglu(c):
     close(y, val * F.gelu(gate), f"geglu C={c}")
 
 
-@pytest.mark.parametrize("n,h,w,cin,cout", [(3, 9, 16, 64, 128), (2, 16, 128, 128, 320), (2, 5, 8, 64, 64), (1, 2, 4, 128, 64), (2, 72, 128, 64, 32)])
+@pytest.mark.parametrize("n,h,w,cin,cout", [(3, 9, 16, 64, 128), (2, 16, 128, 128, 320), (2, 5, 8, 64, 64), (1, 2, 4, 128, 64), (2, 72, 128, 64, 32), (2, 18, 32, 128, 640)])
 def test_conv3x3(n, h, w, cin, cout):
     x = rnd(n, h, w, cin, seed=1).half().to(DEV)
     wt, b = rnd(cout, cin, 3, 3, seed=2, scale=(9 * cin) ** -0.5), rnd(cout, seed=3)

@@ -141,29 +141,38 @@ attn_spatial_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
 
     if (warp == 0) {
         // ================================ TMA producer ================================
-        if (lane == 0) {
+        // whole warp in the loop, one elected lane issues (a TMA / tcgen05 instruction under a divergent `lane == 0`
+        // branch gets an ELECT + BRA.U.ANY serialisation loop from ptxas: ~100 cycles each, profiles/r01_mma_cost.md)
+        if (elect_one()) {
             mbar_expect_tx(bar_q, 2 * kTileBytes);
             tma_load_3d(sQ, &tm_qkv, bar_q, head * kD, q0, img);
             tma_load_3d(sQ + kTileBytes, &tm_qkv, bar_q, head * kD, q0 + kQ, img);
-            for (int i = 0; i < 2 * nkv; ++i) {                 // item 2j = K_j, 2j+1 = V_j
-                const int st = i % kRing;
-                mbar_wait(bar_empty + 8 * st, ((uint32_t)(i / kRing) & 1u) ^ 1u);
+        }
+        __syncwarp();
+        for (int i = 0; i < 2 * nkv; ++i) {                     // item 2j = K_j, 2j+1 = V_j
+            const int st = i % kRing;
+            mbar_wait(bar_empty + 8 * st, ((uint32_t)(i / kRing) & 1u) ^ 1u);
+            if (elect_one()) {
                 mbar_expect_tx(bar_full + 8 * st, kTileBytes);
                 const int col = ((i & 1) ? 2 * C : C) + head * kD;
                 tma_load_3d(sRing + st * kTileBytes, &tm_qkv, bar_full + 8 * st, col, (i >> 1) * kKV, img);
             }
+            __syncwarp();
         }
     } else if (warp == 1) {
         // ================================ MMA issuer ================================
-        if (lane == 0) {
+        {
             const uint32_t idesc_qk = make_idesc_f16(kKV, 0, 0);
             const uint32_t idesc_pv = make_idesc_f16(kOCols, 0, 1);           // B (= [V | ones]) is MN-major, N = 80
             auto issue_qk = [&](int t, int stage) {
                 const uint64_t dq = make_desc_sw128(sQ + t * kTileBytes), dk = make_desc_sw128(sRing + stage * kTileBytes);
+                if (elect_one()) {
 #pragma unroll
-                for (int kk = 0; kk < kD / 16; ++kk)
-                    umma_f16_ss(tmem_base + t * 128, dq + 2 * kk, dk + 2 * kk, idesc_qk, kk > 0 ? 1u : 0u);
-                umma_commit(bar_s_full + 8 * t);
+                    for (int kk = 0; kk < kD / 16; ++kk)
+                        umma_f16_ss(tmem_base + t * 128, dq + 2 * kk, dk + 2 * kk, idesc_qk, kk > 0 ? 1u : 0u);
+                    umma_commit(bar_s_full + 8 * t);
+                }
+                __syncwarp();
             };
             auto issue_pv = [&](int t, int stage, bool first) {
                 // MN-major B: N-atom 0 (columns 0..63) = the V tile, N-atom 1 (columns 64..79) = the ones tile at +LBO;
@@ -171,19 +180,24 @@ attn_spatial_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
                 const uint32_t v_addr = sRing + stage * kTileBytes;
                 const uint64_t dv = (uint64_t((v_addr & 0x3FFFF) >> 4)) | (uint64_t((sOnes - v_addr) >> 4) << 16) |
                                     (uint64_t(1024 >> 4) << 32) | (uint64_t(1) << 46) | (uint64_t(2) << 61);
+                const uint64_t dp0 = make_desc_sw128(sP + t * 2 * kTileBytes);
+                if (elect_one()) {
 #pragma unroll
-                for (int kk = 0; kk < kKV / 16; ++kk) {
-                    const uint64_t dp = make_desc_sw128(sP + t * 2 * kTileBytes + (kk >> 2) * kTileBytes) + 2 * (kk & 3);
-                    umma_f16_ss(tmem_base + 256 + t * 128, dp, dv + (uint64_t)kk * (2048 >> 4), idesc_pv, (!first || kk > 0) ? 1u : 0u);
+                    for (int kk = 0; kk < kKV / 16; ++kk) {
+                        const uint64_t dp = dp0 + (uint64_t)((kk >> 2) * (kTileBytes >> 4) + 2 * (kk & 3));
+                        umma_f16_ss(tmem_base + 256 + t * 128, dp, dv + (uint64_t)kk * (2048 >> 4), idesc_pv, (!first || kk > 0) ? 1u : 0u);
+                    }
+                    umma_commit(bar_pv_done + 8 * t);
                 }
-                umma_commit(bar_pv_done + 8 * t);
+                __syncwarp();
             };
             mbar_wait(bar_q, 0);
             mbar_wait(bar_full + 0, 0);                                       // K_0 in ring slot 0
             tc_fence_after();
             issue_qk(0, 0);
             issue_qk(1, 0);
-            umma_commit(bar_empty + 0);
+            if (elect_one()) umma_commit(bar_empty + 0);
+            __syncwarp();
             for (int j = 0; j < nkv; ++j) {
                 const bool more = (j + 1 < nkv);
                 const int ik = 2 * j + 2, iv = 2 * j + 1;
@@ -200,8 +214,11 @@ attn_spatial_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
                     tc_fence_after();
                     issue_pv(t, sv, j == 0);
                 }
-                if (more) umma_commit(bar_empty + 8 * sk);
-                umma_commit(bar_empty + 8 * sv);
+                if (elect_one()) {
+                    if (more) umma_commit(bar_empty + 8 * sk);
+                    umma_commit(bar_empty + 8 * sv);
+                }
+                __syncwarp();
             }
         }
     } else {

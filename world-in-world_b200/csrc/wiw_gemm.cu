@@ -36,12 +36,16 @@ struct GemmArgs {
     int bn, stages, num_taps, chunks_per_tap;
     int out_cols_per_tile, geglu, has_res, has_aux;
     int tab_div, tab_mod, n_total, tmem_cols;
-    int tab_stride, act;
+    int tab_stride, act, out_total;
+    int dbg;                                      // development aid: bit 0 = skip TMA loads, bit 1 = skip MMA issue (timing only)
     const float* bias;
     const __half* tab;
     float s_acc, s_res, s_aux;
     int tap_cbase[9], tap_ox[9], tap_p[9], tap_oy[9];
 };
+
+// development aid (WIW_GEMM_DBG bit 2): cycle counters of CTA 0's producer / MMA / first epilogue warp, read by wiw_debug_gemm_prof
+__device__ long long g_gemm_prof[8];
 
 struct TileCoord {
     int x0, y0, img, n_tile;
@@ -129,19 +133,30 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 
     if (warp == 0) {
         // ================================ TMA producer ================================
-        if (lane == 0) {
-            int s = 0;
-            uint32_t ph = 0;
-            for (int tile = first_tile; tile < g.total_tiles; tile += tile_step) {
-                const TileCoord t = decode_tile<CG>(g, tile, cta_rank);
-                const int n0 = t.n_tile * g.bn + cta_rank * (g.bn / CG);
-                int kcol = 0;
-                for (int tap = 0; tap < g.num_taps; ++tap) {
-                    const int cb = g.tap_cbase[tap], cx = t.x0 + g.tap_ox[tap], cp = g.tap_p[tap], cy = t.y0 + g.tap_oy[tap];
-                    for (int ch = 0; ch < g.chunks_per_tap; ++ch) {
-                        mbar_wait(bar_empty + 8 * s, ph ^ 1);
-                        const uint32_t sa = smem_base + s * stage_bytes;
-                        if (CG == 2) {
+        // The whole warp runs the loop (warp-uniform control flow) and ONE elected lane issues: a TMA / tcgen05
+        // instruction reached under a divergent `lane == 0` branch is wrapped by ptxas in an ELECT + BRA.U.ANY
+        // serialisation loop with its operands moved through R2UR, which costs ~100 cycles per instruction
+        // (profiles/r01_mma_cost.md); from a converged warp the UTMALDG / UTCHMMA / UTCBAR are issued back to back.
+        int s = 0;
+        uint32_t ph = 0;
+        const bool prof = (g.dbg & 4) && blockIdx.x == 0;
+        long long p_wait = 0;
+        const long long p_t0 = prof ? clock64() : 0;
+        for (int tile = first_tile; tile < g.total_tiles; tile += tile_step) {
+            const TileCoord t = decode_tile<CG>(g, tile, cta_rank);
+            const int n0 = t.n_tile * g.bn + cta_rank * (g.bn / CG);
+            int kcol = 0;
+            for (int tap = 0; tap < g.num_taps; ++tap) {
+                const int cb = g.tap_cbase[tap], cx = t.x0 + g.tap_ox[tap], cp = g.tap_p[tap], cy = t.y0 + g.tap_oy[tap];
+                for (int ch = 0; ch < g.chunks_per_tap; ++ch) {
+                    const long long w0 = prof ? clock64() : 0;
+                    mbar_wait(bar_empty + 8 * s, ph ^ 1);
+                    if (prof) p_wait += clock64() - w0;
+                    const uint32_t sa = smem_base + s * stage_bytes;
+                    if (elect_one()) {
+                        if (g.dbg & 1) {
+                            if (cta_rank == 0) mbar_arrive(bar_full + 8 * s);
+                        } else if (CG == 2) {
                             // both CTAs' bytes are credited to the leader's barrier; only the leader arms it
                             if (cta_rank == 0) mbar_expect_tx(bar_full + 8 * s, 2 * stage_bytes);
                             tma_load_5d_2sm(sa, &tm_a, bar_full + 8 * s, cb + ch * kBlockK, cx, cp, cy, t.img);
@@ -151,59 +166,80 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                             tma_load_5d(sa, &tm_a, bar_full + 8 * s, cb + ch * kBlockK, cx, cp, cy, t.img);
                             tma_load_2d(sa + a_bytes, &tm_b, bar_full + 8 * s, kcol, n0);
                         }
-                        kcol += kBlockK;
-                        if (++s == g.stages) { s = 0; ph ^= 1; }
                     }
+                    __syncwarp();
+                    kcol += kBlockK;
+                    if (++s == g.stages) { s = 0; ph ^= 1; }
                 }
             }
         }
+        if (prof && lane == 0) { g_gemm_prof[4] = clock64() - p_t0; g_gemm_prof[5] = p_wait; }
     } else if (warp == 1) {
         // ================================ MMA issuer ================================
-        if (lane == 0 && cta_rank == 0) {                 // the leader CTA issues the MMAs of the pair
+        if (cta_rank == 0) {                              // the leader CTA issues the MMAs of the pair
             const uint32_t idesc = make_idesc_f16(g.bn, 0, 0, 128 * CG);
             int s = 0;
             uint32_t ph = 0;
             int as = 0;
             uint32_t aph = 0;
+            const bool prof = (g.dbg & 4) && blockIdx.x == 0;
+            long long m_wfull = 0, m_wacc = 0, m_steps = 0;
+            const long long m_t0 = prof ? clock64() : 0;
             for (int tile = first_tile; tile < g.total_tiles; tile += tile_step) {
+                const long long w0 = prof ? clock64() : 0;
                 mbar_wait(bar_tempty + 8 * as, aph ^ 1);
+                if (prof) m_wacc += clock64() - w0;
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + as * acc_stride;
                 for (int it = 0; it < k_iters; ++it) {
+                    const long long w1 = prof ? clock64() : 0;
                     mbar_wait(bar_full + 8 * s, ph);
+                    if (prof) { m_wfull += clock64() - w1; ++m_steps; }
                     tc_fence_after();
                     const uint32_t sa = smem_base + s * stage_bytes;
                     const uint64_t da = make_desc_sw128(sa);
                     const uint64_t db = make_desc_sw128(sa + a_bytes);
+                    if (elect_one()) {                    // converged warp, one issuing lane (see the producer's note)
+                        if (!(g.dbg & 2)) {
 #pragma unroll
-                    for (int kk = 0; kk < kBlockK / 16; ++kk) {
-                        // +32 bytes per K=16 step inside the 128-byte swizzle row (units of 16 B)
-                        if (CG == 2) umma_f16_ss_2sm(d_tmem, da + 2 * kk, db + 2 * kk, idesc, (it > 0 || kk > 0) ? 1u : 0u);
-                        else umma_f16_ss(d_tmem, da + 2 * kk, db + 2 * kk, idesc, (it > 0 || kk > 0) ? 1u : 0u);
+                            for (int kk = 0; kk < kBlockK / 16; ++kk) {
+                                // +32 bytes per K=16 step inside the 128-byte swizzle row (units of 16 B)
+                                if (CG == 2) umma_f16_ss_2sm(d_tmem, da + 2 * kk, db + 2 * kk, idesc, (it > 0 || kk > 0) ? 1u : 0u);
+                                else umma_f16_ss(d_tmem, da + 2 * kk, db + 2 * kk, idesc, (it > 0 || kk > 0) ? 1u : 0u);
+                            }
+                        }
+                        // frees the smem stage (in both CTAs of a pair) when the MMAs retire
+                        if (CG == 2) umma_commit_2sm(bar_empty + 8 * s, 3); else umma_commit(bar_empty + 8 * s);
+                        if (it == k_iters - 1) {          // accumulator ready
+                            if (CG == 2) umma_commit_2sm(bar_tfull + 8 * as, 3); else umma_commit(bar_tfull + 8 * as);
+                        }
                     }
-                    // frees the smem stage (in both CTAs of a pair) when the MMAs retire
-                    if (CG == 2) umma_commit_2sm(bar_empty + 8 * s, 3); else umma_commit(bar_empty + 8 * s);
+                    __syncwarp();
                     if (++s == g.stages) { s = 0; ph ^= 1; }
                 }
-                if (CG == 2) umma_commit_2sm(bar_tfull + 8 * as, 3); else umma_commit(bar_tfull + 8 * as);   // accumulator ready
                 if (++as == 2) { as = 0; aph ^= 1; }
             }
+            if (prof && lane == 0) { g_gemm_prof[0] = clock64() - m_t0; g_gemm_prof[1] = m_wfull; g_gemm_prof[2] = m_wacc; g_gemm_prof[3] = m_steps; }
         }
     } else if (warp == 2) {
         // ================================ epilogue loader ================================
-        if (has_epi_loads && lane == 0) {
-            const int chunks = g.out_cols_per_tile / kEpiCols;
+        if (has_epi_loads) {
+            const int full_chunks = g.out_cols_per_tile / kEpiCols;
             const uint32_t bytes = kEpiChunkBytes * ((g.has_res ? 1 : 0) + (g.has_aux ? 1 : 0));
             int rs = 0;
             uint32_t rph = 0;
             for (int tile = first_tile; tile < g.total_tiles; tile += tile_step) {
                 const TileCoord t = decode_tile<CG>(g, tile, cta_rank);
                 const int c0 = t.n_tile * g.out_cols_per_tile;
+                const int chunks = min(full_chunks, (g.out_total - c0) / kEpiCols);     // the last N-tile may be ragged
                 for (int j = 0; j < chunks; ++j) {
                     mbar_wait(bar_rempty + 8 * rs, rph ^ 1);
-                    mbar_expect_tx(bar_rfull + 8 * rs, bytes);
-                    if (g.has_res) tma_load_4d(res_base + rs * kEpiChunkBytes, &tm_res, bar_rfull + 8 * rs, c0 + j * kEpiCols, t.x0, t.y0, t.img);
-                    if (g.has_aux) tma_load_4d(aux_base + rs * kEpiChunkBytes, &tm_aux, bar_rfull + 8 * rs, c0 + j * kEpiCols, t.x0, t.y0, t.img);
+                    if (elect_one()) {
+                        mbar_expect_tx(bar_rfull + 8 * rs, bytes);
+                        if (g.has_res) tma_load_4d(res_base + rs * kEpiChunkBytes, &tm_res, bar_rfull + 8 * rs, c0 + j * kEpiCols, t.x0, t.y0, t.img);
+                        if (g.has_aux) tma_load_4d(aux_base + rs * kEpiChunkBytes, &tm_aux, bar_rfull + 8 * rs, c0 + j * kEpiCols, t.x0, t.y0, t.img);
+                    }
+                    __syncwarp();
                     if (++rs == kResSlots) { rs = 0; rph ^= 1; }
                 }
             }
@@ -216,8 +252,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         const int grp = (warp - 3) >> 2;
         const int q = warp & 3;                        // TMEM lane quadrant this warp may access
         const int row = q * 32 + lane;                 // row of the 128-row tile == TMEM lane
-        const bool store_leader = (((warp - 3) & 3) == 0 && lane == 0);
-        const int chunks = g.out_cols_per_tile / kEpiCols;
+        const bool store_warp = (((warp - 3) & 3) == 0);   // its elected lane owns the group's bulk-store groups (elect.sync is deterministic)
+        const int full_chunks = g.out_cols_per_tile / kEpiCols;
         const uint32_t sw = (uint32_t(row) >> 1) & 3u;  // SWIZZLE_64B: 16-B chunk index ^= (row>>1)&3
         const uint32_t row_off = uint32_t(row) * 64u;
         const uint32_t bar_id = 1 + grp;
@@ -225,10 +261,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         uint32_t aph = 0;
         int ob = 0;                                    // this group's staging buffer (2 per group)
         long long chunk_base = 0;                      // chunks consumed by this CTA before the current tile
+        int chunks = 0;
+        const bool eprof = (g.dbg & 4) && blockIdx.x == 0 && warp == 3;
+        long long e_wait = 0;
+        const long long e_t0 = eprof ? clock64() : 0;
         for (int tile = first_tile; tile < g.total_tiles; tile += tile_step, chunk_base += chunks) {
             const TileCoord t = decode_tile<CG>(g, tile, cta_rank);
             const int acc_n0 = t.n_tile * g.bn;                       // first GEMM column of this tile
             const int out_c0 = t.n_tile * g.out_cols_per_tile;        // first output channel
+            chunks = min(full_chunks, (g.out_total - out_c0) / kEpiCols);      // ragged last N-tile: padded columns are skipped
             const __half* tab_row = nullptr;
             if (g.tab != nullptr) {
                 const int x = t.x0 + (row % g.bx), y = t.y0 + (row / g.bx);
@@ -237,7 +278,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 int gi = int((grow / g.tab_div) % g.tab_mod);
                 tab_row = g.tab + (size_t)gi * g.tab_stride;
             }
+            const long long e0 = (eprof) ? clock64() : 0;
             mbar_wait(bar_tfull + 8 * as, aph);
+            if (eprof) e_wait += clock64() - e0;
             tc_fence_after();
             const uint32_t t_acc = tmem_base + as * acc_stride + (uint32_t(q * 32) << 16);
             const int last_j = ((chunks - 1 - grp) >= 0) ? (grp + 2 * ((chunks - 1 - grp) / 2)) : -1;
@@ -342,7 +385,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 }
                 // The store issued two chunks ago by this group read the buffer we are about to overwrite:
                 // the leader waits until at most one of its bulk groups is still reading, then releases the group.
-                if (store_leader) tma_store_wait_read<1>();
+                if (store_warp) { if (elect_one()) tma_store_wait_read<1>(); __syncwarp(); }
                 asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
                 {
                     uint8_t* p = smem_raw + (out_base - smem_u32(smem_raw)) + (grp * 2 + ob) * kEpiChunkBytes + row_off;
@@ -357,15 +400,19 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 }
                 fence_proxy_async_smem();
                 asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
-                if (store_leader) {
-                    tma_store_4d(&tm_out, out_base + (grp * 2 + ob) * kEpiChunkBytes, out_c0 + j * kEpiCols, t.x0, t.y0, t.img);
-                    tma_store_commit();
+                if (store_warp) {
+                    if (elect_one()) {
+                        tma_store_4d(&tm_out, out_base + (grp * 2 + ob) * kEpiChunkBytes, out_c0 + j * kEpiCols, t.x0, t.y0, t.img);
+                        tma_store_commit();
+                    }
+                    __syncwarp();
                 }
                 ob ^= 1;
             }
             if (++as == 2) { as = 0; aph ^= 1; }
         }
-        if (store_leader) tma_store_wait_all<0>();
+        if (store_warp) { if (elect_one()) tma_store_wait_all<0>(); __syncwarp(); }
+        if (eprof && lane == 0) { g_gemm_prof[7] = clock64() - e_t0; g_gemm_prof[6] = e_wait; }
     }
 
     tc_fence_before();
@@ -384,7 +431,8 @@ static int launch_conv_gemm(const wiw_gemm_desc* d, cudaStream_t stream) {
     WIW_REQUIRE(d->bx > 0 && d->by > 0 && d->bx * d->by == kBlockM, "bx*by must be 128");
     WIW_REQUIRE(d->bn >= 32 && d->bn <= 256 && d->bn % 32 == 0, "bn must be a multiple of 32 in [32,256]");
     WIW_REQUIRE(!d->geglu || d->bn % 64 == 0, "geglu needs bn % 64 == 0");
-    WIW_REQUIRE(d->n_total % d->bn == 0, "n_total must be a multiple of bn");
+    WIW_REQUIRE(d->n_total % 32 == 0, "n_total must be a multiple of 32");
+    WIW_REQUIRE(!d->geglu || d->n_total % d->bn == 0, "geglu needs n_total to be a multiple of bn");
     WIW_REQUIRE(d->num_taps >= 1 && d->num_taps <= 9 && d->chunks_per_tap >= 1, "bad tap spec");
     WIW_REQUIRE(d->k_total == (int64_t)d->num_taps * d->chunks_per_tap * kBlockK, "k_total != taps*chunks*64");
     const int64_t out_c = d->geglu ? d->n_total / 2 : d->n_total;
@@ -401,25 +449,27 @@ static int launch_conv_gemm(const wiw_gemm_desc* d, cudaStream_t stream) {
     g.dim_x = (int)d->out_dim[1]; g.dim_y = (int)d->out_dim[2];
     g.tiles_x = (g.dim_x + g.bx - 1) / g.bx;
     g.tiles_y = (g.dim_y + g.by - 1) / g.by;
-    g.n_tiles = (int)(d->n_total / d->bn);
+    g.n_tiles = (int)((d->n_total + d->bn - 1) / d->bn);          // a ragged last N-tile loads zero rows (TMA OOB fill) and skips its padded columns
     const long long m_tiles = (long long)g.tiles_x * g.tiles_y * d->out_dim[3];
     WIW_REQUIRE(m_tiles * g.n_tiles < (1LL << 31), "too many tiles");
     // CTA pairs (cta_group::2, M = 256 per MMA, each CTA stages half of the weight tile) whenever the problem
     // fills the machine; small problems keep single-CTA tiles
     static const int force_cg = getenv("WIW_GEMM_CG") ? atoi(getenv("WIW_GEMM_CG")) : 0;      // development aid for A/B runs
-    // Measured on B200 (profiles/r01_gemm_pair_ab.md): pairs win when the reduction is long enough to amortise the
-    // cross-CTA handshakes -- plain GEMMs with K >= 1280, N-tile-256 problems with K >= 640, convs with >= 960 input
-    // channels -- and lose a few % on the short-K projections and the 320/640-channel convs.
-    const bool pair_shape = (d->k_total >= 1280) && (d->num_taps == 1 || d->bn == 256 || d->chunks_per_tap >= 15);
+    // Measured on B200 (profiles/r01_mma_cost.md, r01_gemm_pair_ab.md): a single-CTA tile is bound by shared-memory
+    // bandwidth (TMA writes + UMMA reads of the same stage, 128 B/clk), so halving the weight bytes per CTA wins on
+    // every shape except the tiny K=320, N=320 projection, where the pair handshakes cost ~3 %.
+    const bool pair_shape = !(d->k_total <= 320 && d->n_total <= 320);
     int cg = (pair_shape && m_tiles * g.n_tiles >= 2LL * num_sms()) ? 2 : 1;
     if (force_cg == 1 || force_cg == 2) cg = force_cg;
     g.total_tiles = (int)(((m_tiles + cg - 1) / cg) * g.n_tiles);
+    static const int dbg = getenv("WIW_GEMM_DBG") ? atoi(getenv("WIW_GEMM_DBG")) : 0;
+    g.dbg = dbg;
     g.bn = d->bn;
     g.num_taps = d->num_taps; g.chunks_per_tap = d->chunks_per_tap;
     g.geglu = d->geglu ? 1 : 0;
     g.out_cols_per_tile = g.geglu ? d->bn / 2 : d->bn;
     g.has_res = d->res ? 1 : 0; g.has_aux = d->aux ? 1 : 0;
-    g.tab_div = d->tab_div; g.tab_mod = d->tab_mod; g.n_total = (int)d->n_total;
+    g.tab_div = d->tab_div; g.tab_mod = d->tab_mod; g.n_total = (int)d->n_total; g.out_total = (int)out_c;
     g.tab_stride = d->tab_stride > 0 ? d->tab_stride : (int)d->n_total; g.act = d->act;
     g.bias = d->bias; g.tab = static_cast<const __half*>(d->tab);
     g.s_acc = d->s_acc; g.s_res = d->s_res; g.s_aux = d->s_aux;
@@ -496,6 +546,10 @@ static int launch_conv_gemm(const wiw_gemm_desc* d, cudaStream_t stream) {
 }
 
 }  // namespace wiw
+
+extern "C" int wiw_debug_gemm_prof(long long* out8) {
+    return cudaMemcpyFromSymbol(out8, wiw::g_gemm_prof, 8 * sizeof(long long)) == cudaSuccess ? 0 : 1;
+}
 
 extern "C" int wiw_conv_gemm(const wiw_gemm_desc* d, wiw_stream_t stream) {
     return wiw::launch_conv_gemm(d, static_cast<cudaStream_t>(stream));

@@ -30,11 +30,22 @@ class GemmWeight:
 
 
 def pick_bn(n: int, geglu: bool = False) -> int:
+    """N-tile width.  Measured on B200 (profiles/r01_mma_cost.md): an SS-mode tcgen05.mma with M=128 costs the same
+    ~128 cycles for every N <= 256, so the cheapest tiling is the one with the FEWEST N-tiles; among those the
+    narrowest width (least padding, most pipeline stages).  The last tile may be ragged (the kernel zero-fills and
+    skips its padded columns); GEGLU tiles must divide N because value/gate columns are interleaved per tile."""
     step = 64 if geglu else 32
-    for bn in range(256, 0, -step):
-        if n % bn == 0:
+    if n % step:
+        raise ValueError(f"N={n} is not a multiple of {step}")
+    if geglu:
+        for bn in range(256, 0, -step):
+            if n % bn == 0:
+                return bn
+    tiles = -(-n // 256)
+    for bn in range(step, 257, step):
+        if -(-n // bn) == tiles:
             return bn
-    raise ValueError(f"N={n} is not a multiple of {step}")
+    raise AssertionError
 
 
 def _pad_to(x: int, m: int) -> int:
