@@ -155,6 +155,8 @@ def main():
     ap.add_argument("--impl", default="wiw", choices=["wiw", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--profiler-range", action="store_true",
+                    help="cudaProfilerStart/Stop around the timed region (for `ncu --profile-from-start off`)")
     args = ap.parse_args()
     rank, local, world = int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     if args.impl == "reference":
@@ -215,11 +217,15 @@ def main():
         sampler.start()
     L.COUNTERS["gpu_launches"] = 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if args.profiler_range:
+        torch.cuda.profiler.start()
     e0.record()
     for _ in range(args.steps):
         step()
     e1.record()
     barrier()
+    if args.profiler_range:
+        torch.cuda.profiler.stop()
     launches = L.COUNTERS["gpu_launches"]
     clocks = sampler.stop() if sampler else None
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
