@@ -48,7 +48,8 @@ def test_request_checks_and_name_matching():
     with pytest.raises(AssertionError):
         W.check_inputdict({**ok, "b_image": np.zeros((1, 3, 8, 8), np.float32)})
     assert W.name_matches("igen", "igen") and W.name_matches("i", "igen") and W.name_matches("ig", "igen")
-    assert not W.name_matches("cosmos", "igen") and not W.name_matches("", "igen") and not W.name_matches(None, "igen")
+    assert W.name_matches("g", "igen") and W.name_matches("en", "igen") and W.name_matches("", "igen")     # Batcher slices
+    assert not W.name_matches("cosmos", "igen") and not W.name_matches("c", "igen") and not W.name_matches(None, "igen")
     with pytest.raises(AssertionError):
         W.check_outputdict({"pred_frames": np.zeros((1,), np.float32), "save_dirs": []})
     with pytest.raises(AssertionError):

@@ -13,7 +13,7 @@ script -- see INTEGRATION.md.
 
 Deliberate deviations from the shipped reference, each fixing a latent defect listed in SURVEY.md section 0:
   - world_model_name is defined ("igen", downstream/vlm.py:31) and a name sliced by the manager's Batcher
-    (worker_manager.py:457-458) is accepted when it is a prefix of it;
+    (worker_manager.py:457-458: "i", "g", "e", "n", "" ...) is accepted when it is a contiguous slice of it;
   - RGBA observations are sliced to RGB (the reference pipeline fails on 4-channel PIL images);
   - an exception inside the task is caught, logged and answered with well-formed zero frames instead of
     killing the worker (the manager has no error channel, worker_manager.py:369-379).
@@ -140,8 +140,12 @@ def action_ids_idx_encode(actions: np.ndarray) -> torch.Tensor:
 
 
 def name_matches(request_name, deployed: str) -> bool:
-    """api_models/__init__.py:189 with the Batcher string-slicing defect tolerated."""
-    return isinstance(request_name, str) and len(request_name) > 0 and (request_name == deployed or deployed.startswith(request_name))
+    """api_models/__init__.py:189 with the Batcher string-slicing defect tolerated: the manager's
+    Batcher slices EVERY request value with v[start:start+bs] (worker_manager.py:457-458), so sub-batch k of an
+    "igen" request carries request_model_name == "igen"[k*bs:(k+1)*bs] -- "i", "g", "e", "n", then "" for k >= 4
+    (found by running the reference's own manager against this worker, tests/test_reference_manager_interop_cpu.py).
+    Accepted: the full name or any contiguous slice of it (including the empty tail slice)."""
+    return isinstance(request_name, str) and request_name in deployed
 
 
 def images_to_tensor(frames_u8: np.ndarray, save_size) -> torch.Tensor:
