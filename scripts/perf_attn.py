@@ -25,14 +25,16 @@ x = torch.randn(8192, 8192, device=DEV).half(); w = torch.randn(8192, 8192, devi
 ref = timeit(lambda: torch.matmul(x, w.t()))
 print(f"cublas 8192^3: {ref:.4f} ms ({2*8192**3/ref/1e9:.0f} TFLOP/s)", flush=True)
 del x, w
-for (imgs, s, c) in [(28, 9216, 320), (28, 2304, 640), (28, 576, 1280)]:
+NORM_ONLY = "norm" in sys.argv
+for (imgs, s, c) in [(28, 9216, 320), (28, 2304, 640), (28, 576, 1280), (28, 144, 1280), (28, 9216, 960)]:
     qkv = torch.randn(imgs * s, 3 * c, device=DEV).half()
     out = torch.empty(imgs * s, c, device=DEV, dtype=torch.half)
-    ms = timeit(lambda: ops.attention_spatial(qkv, imgs, s, c, out=out))
-    fl = 4.0 * imgs * (c // 64) * s * s * 64
-    print(f"attn_spatial imgs={imgs} S={s} C={c}: {ms:.4f} ms  {fl/ms/1e9:.0f} TFLOP/s", flush=True)
-    ms = timeit(lambda: ops.attention_temporal(qkv, 2, 14, s, c, out=out))
-    print(f"attn_temporal S={s} C={c}: {ms:.4f} ms  {(qkv.numel()+out.numel())*2/ms/1e6:.0f} GB/s", flush=True)
+    if not NORM_ONLY and c <= 1280 and s >= 576:
+        ms = timeit(lambda: ops.attention_spatial(qkv, imgs, s, c, out=out))
+        fl = 4.0 * imgs * (c // 64) * s * s * 64
+        print(f"attn_spatial imgs={imgs} S={s} C={c}: {ms:.4f} ms  {fl/ms/1e9:.0f} TFLOP/s", flush=True)
+        ms = timeit(lambda: ops.attention_temporal(qkv, 2, 14, s, c, out=out))
+        print(f"attn_temporal S={s} C={c}: {ms:.4f} ms  {(qkv.numel()+out.numel())*2/ms/1e6:.0f} GB/s", flush=True)
     xin = torch.randn(imgs * s, c, device=DEV).half()
     nw = ops.prep_norm(torch.ones(c), torch.zeros(c), DEV)
     ms = timeit(lambda: ops.layer_norm(xin, nw, out=out))

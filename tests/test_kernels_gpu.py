@@ -30,7 +30,10 @@ def close(y, ref, what="", rel=2e-3, abs_scale=2e-3):
 
 
 @pytest.mark.parametrize("samples,rows,c,silu", [(3, 144, 64, True), (28, 576, 320, True), (2, 14 * 144, 960, False),
-                                                 (2, 37, 1920, True), (1, 5000, 128, False)])
+                                                 (2, 37, 1920, True), (1, 5000, 128, False),
+                                                 # many tiles per CTA: the 4-stage TMA ring of the streaming kernels wraps several times
+                                                 (2, 60000, 320, True), (3, 20011, 640, False), (1, 9000, 1280, True),
+                                                 (2, 300, 2560, True)])
 def test_groupnorm(samples, rows, c, silu):
     x = (rnd(samples, rows, c, seed=1) * 2 + 0.7).half().to(DEV)
     g, b = 1 + 0.1 * rnd(c, seed=2), 0.1 * rnd(c, seed=3)
@@ -42,7 +45,8 @@ def test_groupnorm(samples, rows, c, silu):
     close(y, ref.permute(0, 2, 1), f"gn {samples}x{rows}x{c}")
 
 
-@pytest.mark.parametrize("m,c", [(1000, 64), (333, 320), (50, 640), (7, 1280), (4100, 128)])
+@pytest.mark.parametrize("m,c", [(1000, 64), (333, 320), (50, 640), (7, 1280), (4100, 128),
+                                 (120001, 320), (40000, 640), (20003, 1280), (3000, 2048)])     # ring wraps several times
 def test_layernorm(m, c):
     x = (rnd(m, c, seed=1) * 3 + 1).half().to(DEV)
     g, b = 1 + 0.1 * rnd(c, seed=2), 0.1 * rnd(c, seed=3)

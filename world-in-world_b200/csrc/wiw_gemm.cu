@@ -9,7 +9,8 @@
 //   warp 2      TMEM allocator + TMA loader of the epilogue's residual / aux tiles
 //   warps 3-10  epilogue, two groups of 4 warps on alternating 32-column chunks: tcgen05.ld -> (bias,
 //               per-row-group table, SiLU, GEGLU, residual blend) -> fp16 -> swizzled smem -> TMA store
-//               (clips partial tiles)
+//               (clips partial tiles).  Every warp stages and stores its OWN 32-row slab (2 KB, its own
+//               bulk-store groups), so the epilogue warps never meet at a CTA barrier.
 //
 // Pipelines: smem full/empty ring (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue),
 // residual full/empty ring (loader <-> epilogue), bulk-group ring for the stores.
@@ -38,6 +39,8 @@ struct GemmArgs {
     int tab_div, tab_mod, n_total, tmem_cols;
     int tab_stride, act, out_total;
     int dbg;                                      // development aid: bit 0 = skip TMA loads, bit 1 = skip MMA issue (timing only)
+    int warp_store;                               // 1: every epilogue warp stores its own 32-row slab (no CTA barriers); 0: one store per 128-row chunk
+    int wx0[4], wy0[4];                           // pixel offset of epilogue warp q's 32 rows inside the bx x by tile
     const float* bias;
     const __half* tab;
     float s_acc, s_res, s_aux;
@@ -67,11 +70,12 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmArgs& g, int tile, in
     return t;
 }
 
-template <int CG>
+template <int CG, bool GEGLU>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
-                 const __grid_constant__ CUtensorMap tm_out, const __grid_constant__ CUtensorMap tm_res,
-                 const __grid_constant__ CUtensorMap tm_aux, const __grid_constant__ GemmArgs g) {
+                 const __grid_constant__ CUtensorMap tm_out /* box = one warp's 32 rows x 32 channels */,
+                 const __grid_constant__ CUtensorMap tm_res, const __grid_constant__ CUtensorMap tm_aux,
+                 const __grid_constant__ GemmArgs g) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // carve: [stages x (A 16 KB | B bn*128)] [out bufs] [res slots] [aux slots] [barriers]
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -291,25 +295,38 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             }
             for (int j = grp; j < chunks; j += 2) {
                 float v[kEpiCols];
+                uint32_t rg[kEpiCols];                              // gate half of a GEGLU tile
+                const int half_n = g.bn >> 1;
                 {
+                    // Global loads of bias / table rows are issued BEFORE tcgen05.wait::ld so their latency overlaps the
+                    // TMEM load's; the GEGLU gate load is issued before the value half is consumed.
                     uint32_t r[kEpiCols];
                     tmem_ld_32x32b_x32(t_acc + j * kEpiCols, r);
-                    tmem_ld_wait();
                     const int nb = acc_n0 + j * kEpiCols;
+                    float4 b4[kEpiCols / 4];
+                    uint4 tu[kEpiCols / 8];
+                    if (g.bias != nullptr) {
+#pragma unroll
+                        for (int c = 0; c < kEpiCols / 4; ++c) b4[c] = __ldg(reinterpret_cast<const float4*>(g.bias + nb) + c);
+                    }
+                    if (!GEGLU && tab_row != nullptr) {
+#pragma unroll
+                        for (int c = 0; c < kEpiCols / 8; ++c) tu[c] = __ldg(reinterpret_cast<const uint4*>(tab_row + nb) + c);
+                    }
+                    tmem_ld_wait();
+                    if (GEGLU) tmem_ld_32x32b_x32(t_acc + half_n + j * kEpiCols, rg);
 #pragma unroll
                     for (int c = 0; c < kEpiCols; ++c) v[c] = __uint_as_float(r[c]);
                     if (g.bias != nullptr) {
 #pragma unroll
                         for (int c = 0; c < kEpiCols; c += 4) {
-                            const float4 b4 = __ldg(reinterpret_cast<const float4*>(g.bias + nb + c));
-                            v[c] += b4.x; v[c + 1] += b4.y; v[c + 2] += b4.z; v[c + 3] += b4.w;
+                            v[c] += b4[c / 4].x; v[c + 1] += b4[c / 4].y; v[c + 2] += b4[c / 4].z; v[c + 3] += b4[c / 4].w;
                         }
                     }
-                    if (tab_row != nullptr) {
+                    if (!GEGLU && tab_row != nullptr) {
 #pragma unroll
                         for (int c = 0; c < kEpiCols; c += 8) {
-                            const uint4 u = __ldg(reinterpret_cast<const uint4*>(tab_row + nb + c));
-                            const __half2* h = reinterpret_cast<const __half2*>(&u);
+                            const __half2* h = reinterpret_cast<const __half2*>(&tu[c / 8]);
 #pragma unroll
                             for (int e = 0; e < 4; ++e) {
                                 const float2 f = __half22float2(h[e]);
@@ -317,24 +334,24 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                             }
                         }
                     }
-                    if (g.act == 1) {
+                    if (!GEGLU && g.act == 1) {
 #pragma unroll
                         for (int c = 0; c < kEpiCols; ++c) v[c] = silu_f(v[c]);
                     }
                 }
-                if (g.geglu) {
-                    uint32_t r[kEpiCols];
-                    const int half_n = g.bn >> 1;
-                    tmem_ld_32x32b_x32(t_acc + half_n + j * kEpiCols, r);
-                    tmem_ld_wait();
+                if (GEGLU) {
                     const int nb = acc_n0 + half_n + j * kEpiCols;
+                    float4 b4[kEpiCols / 4];
+#pragma unroll
+                    for (int c = 0; c < kEpiCols / 4; ++c)
+                        b4[c] = (g.bias != nullptr) ? __ldg(reinterpret_cast<const float4*>(g.bias + nb) + c) : make_float4(0, 0, 0, 0);
+                    tmem_ld_wait();
 #pragma unroll
                     for (int c = 0; c < kEpiCols; c += 4) {
-                        const float4 b4 = (g.bias != nullptr) ? __ldg(reinterpret_cast<const float4*>(g.bias + nb + c)) : make_float4(0, 0, 0, 0);
-                        v[c] *= gelu_fast_f(__uint_as_float(r[c]) + b4.x);
-                        v[c + 1] *= gelu_fast_f(__uint_as_float(r[c + 1]) + b4.y);
-                        v[c + 2] *= gelu_fast_f(__uint_as_float(r[c + 2]) + b4.z);
-                        v[c + 3] *= gelu_fast_f(__uint_as_float(r[c + 3]) + b4.w);
+                        v[c] *= gelu_fast_f(__uint_as_float(rg[c]) + b4[c / 4].x);
+                        v[c + 1] *= gelu_fast_f(__uint_as_float(rg[c + 1]) + b4[c / 4].y);
+                        v[c + 2] *= gelu_fast_f(__uint_as_float(rg[c + 2]) + b4[c / 4].z);
+                        v[c + 3] *= gelu_fast_f(__uint_as_float(rg[c + 3]) + b4[c / 4].w);
                     }
                 }
                 if (j == last_j) {
@@ -385,8 +402,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 }
                 // The store issued two chunks ago by this group read the buffer we are about to overwrite:
                 // the leader waits until at most one of its bulk groups is still reading, then releases the group.
-                if (store_warp) { if (elect_one()) tma_store_wait_read<1>(); __syncwarp(); }
-                asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+                if (g.warp_store) {
+                    if (elect_one()) tma_store_wait_read<1>();
+                    __syncwarp();
+                } else {
+                    if (store_warp) { if (elect_one()) tma_store_wait_read<1>(); __syncwarp(); }
+                    asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+                }
                 {
                     uint8_t* p = smem_raw + (out_base - smem_u32(smem_raw)) + (grp * 2 + ob) * kEpiChunkBytes + row_off;
 #pragma unroll
@@ -399,19 +421,29 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                     }
                 }
                 fence_proxy_async_smem();
-                asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
-                if (store_warp) {
+                if (g.warp_store) {
+                    __syncwarp();                                  // the slab is complete and visible to the async proxy
                     if (elect_one()) {
-                        tma_store_4d(&tm_out, out_base + (grp * 2 + ob) * kEpiChunkBytes, out_c0 + j * kEpiCols, t.x0, t.y0, t.img);
+                        tma_store_4d(&tm_out, out_base + (grp * 2 + ob) * kEpiChunkBytes + q * (32 * 64), out_c0 + j * kEpiCols,
+                                     t.x0 + g.wx0[q], t.y0 + g.wy0[q], t.img);
                         tma_store_commit();
                     }
                     __syncwarp();
+                } else {
+                    asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+                    if (store_warp) {
+                        if (elect_one()) {
+                            tma_store_4d(&tm_out, out_base + (grp * 2 + ob) * kEpiChunkBytes, out_c0 + j * kEpiCols, t.x0, t.y0, t.img);
+                            tma_store_commit();
+                        }
+                        __syncwarp();
+                    }
                 }
                 ob ^= 1;
             }
             if (++as == 2) { as = 0; aph ^= 1; }
         }
-        if (store_warp) { if (elect_one()) tma_store_wait_all<0>(); __syncwarp(); }
+        if (store_warp || g.warp_store) { if (elect_one()) tma_store_wait_all<0>(); __syncwarp(); }
         if (eprof && lane == 0) { g_gemm_prof[7] = clock64() - e_t0; g_gemm_prof[6] = e_wait; }
     }
 
@@ -464,6 +496,10 @@ static int launch_conv_gemm(const wiw_gemm_desc* d, cudaStream_t stream) {
     g.total_tiles = (int)(((m_tiles + cg - 1) / cg) * g.n_tiles);
     static const int dbg = getenv("WIW_GEMM_DBG") ? atoi(getenv("WIW_GEMM_DBG")) : 0;
     g.dbg = dbg;
+    static const int epi = getenv("WIW_GEMM_EPI") ? atoi(getenv("WIW_GEMM_EPI")) : 1;       // development aid for A/B runs
+    g.warp_store = epi ? 1 : 0;
+    const int sbx = d->bx < 32 ? d->bx : 32, sby = 32 / sbx;                                // one warp's 32 rows as a pixel box
+    for (int q = 0; q < 4; ++q) { g.wx0[q] = (q * 32) % d->bx; g.wy0[q] = (q * 32) / d->bx; }
     g.bn = d->bn;
     g.num_taps = d->num_taps; g.chunks_per_tap = d->chunks_per_tap;
     g.geglu = d->geglu ? 1 : 0;
@@ -504,27 +540,30 @@ static int launch_conv_gemm(const wiw_gemm_desc* d, cudaStream_t stream) {
         uint32_t box[2] = {(uint32_t)kBlockK, (uint32_t)(d->bn / cg)};
         if (encode_tmap(&tm_b, d->w, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return 3;
     }
-    auto enc_out = [&](CUtensorMap* m, const void* p, const int64_t* st) -> int {
+    auto enc_out = [&](CUtensorMap* m, const void* p, const int64_t* st, bool warp_box) -> int {
         uint64_t dims[4], strides[3];
-        uint32_t box[4] = {(uint32_t)kEpiCols, (uint32_t)d->bx, (uint32_t)d->by, 1u};
+        uint32_t box[4] = {(uint32_t)kEpiCols, (uint32_t)(warp_box ? sbx : d->bx), (uint32_t)(warp_box ? sby : d->by), 1u};
         for (int i = 0; i < 4; ++i) dims[i] = (uint64_t)d->out_dim[i];
         for (int i = 1; i < 4; ++i) strides[i - 1] = (uint64_t)st[i] * 2;
         return encode_tmap(m, p, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B);
     };
-    if (enc_out(&tm_out, d->out, d->out_stride)) return 3;
-    if (d->res) { if (enc_out(&tm_res, d->res, d->res_stride)) return 3; } else tm_res = tm_out;
-    if (d->aux) { if (enc_out(&tm_aux, d->aux, d->aux_stride)) return 3; } else tm_aux = tm_out;
+    if (enc_out(&tm_out, d->out, d->out_stride, g.warp_store != 0)) return 3;
+    if (d->res) { if (enc_out(&tm_res, d->res, d->res_stride, false)) return 3; } else tm_res = tm_out;
+    if (d->aux) { if (enc_out(&tm_aux, d->aux, d->aux_stride, false)) return 3; } else tm_aux = tm_out;
 
     static bool attr_set = false;
     if (!attr_set) {
-        WIW_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
-        WIW_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+        WIW_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+        WIW_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+        WIW_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+        WIW_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
         attr_set = true;
     }
     if (cg == 1) {
         int grid = num_sms();
         if (grid > g.total_tiles) grid = g.total_tiles;
-        conv_gemm_kernel<1><<<grid, kThreads, smem_bytes, stream>>>(tm_a, tm_b, tm_out, tm_res, tm_aux, g);
+        if (g.geglu) conv_gemm_kernel<1, true><<<grid, kThreads, smem_bytes, stream>>>(tm_a, tm_b, tm_out, tm_res, tm_aux, g);
+        else conv_gemm_kernel<1, false><<<grid, kThreads, smem_bytes, stream>>>(tm_a, tm_b, tm_out, tm_res, tm_aux, g);
     } else {
         int pairs = num_sms() / 2;
         if (pairs > g.total_tiles) pairs = g.total_tiles;
@@ -539,7 +578,8 @@ static int launch_conv_gemm(const wiw_gemm_desc* d, cudaStream_t stream) {
         attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        WIW_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<2>, tm_a, tm_b, tm_out, tm_res, tm_aux, g));
+        if (g.geglu) WIW_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<2, true>, tm_a, tm_b, tm_out, tm_res, tm_aux, g));
+        else WIW_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<2, false>, tm_a, tm_b, tm_out, tm_res, tm_aux, g));
     }
     WIW_CHECK_CUDA(cudaGetLastError());
     return 0;
