@@ -155,6 +155,7 @@ def main():
     ap.add_argument("--impl", default="wiw", choices=["wiw", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--dump-gemm-profile", action="store_true")
     ap.add_argument("--profiler-range", action="store_true",
                     help="cudaProfilerStart/Stop around the timed region (for `ncu --profile-from-start off`)")
     args = ap.parse_args()
@@ -254,6 +255,15 @@ def main():
         prof, ops.PROFILE = ops.PROFILE, None
         g_flop = sum(p[0] for p in prof)
         g_ms = sum(p[1].elapsed_time(p[2]) for p in prof)
+        if args.dump_gemm_profile:                       # per-shape breakdown of the dominant kernel (development aid)
+            by_shape = {}
+            for p in prof:
+                e = by_shape.setdefault(p[3], [0, 0.0, 0.0])
+                e[0] += 1; e[1] += p[0]; e[2] += p[1].elapsed_time(p[2])
+            os.makedirs(os.path.join(REPO, "gpurun_out"), exist_ok=True)
+            with open(os.path.join(REPO, "gpurun_out", "gemm_profile.json"), "w") as f:
+                json.dump([{"shape": k, "launches": v[0], "tflop": v[1] / 1e12, "ms": v[2], "tflops": v[1] / v[2] / 1e9}
+                           for k, v in sorted(by_shape.items(), key=lambda kv: -kv[1][2])], f, indent=1)
         peak, hbm, how = peaks()
         ach = g_flop / (g_ms * 1e-3) / 1e12
         roof = {"bound": "tensor", "kernel": "conv_gemm_kernel (tcgen05 implicit GEMM: all Linear/Conv2d/Conv3d of the UNet)",

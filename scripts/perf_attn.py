@@ -26,6 +26,7 @@ ref = timeit(lambda: torch.matmul(x, w.t()))
 print(f"cublas 8192^3: {ref:.4f} ms ({2*8192**3/ref/1e9:.0f} TFLOP/s)", flush=True)
 del x, w
 NORM_ONLY = "norm" in sys.argv
+ATTN_ONLY = "attn" in sys.argv
 for (imgs, s, c) in [(28, 9216, 320), (28, 2304, 640), (28, 576, 1280), (28, 144, 1280), (28, 9216, 960)]:
     qkv = torch.randn(imgs * s, 3 * c, device=DEV).half()
     out = torch.empty(imgs * s, c, device=DEV, dtype=torch.half)
@@ -35,6 +36,8 @@ for (imgs, s, c) in [(28, 9216, 320), (28, 2304, 640), (28, 576, 1280), (28, 144
         print(f"attn_spatial imgs={imgs} S={s} C={c}: {ms:.4f} ms  {fl/ms/1e9:.0f} TFLOP/s", flush=True)
         ms = timeit(lambda: ops.attention_temporal(qkv, 2, 14, s, c, out=out))
         print(f"attn_temporal S={s} C={c}: {ms:.4f} ms  {(qkv.numel()+out.numel())*2/ms/1e6:.0f} GB/s", flush=True)
+    if ATTN_ONLY:
+        continue
     xin = torch.randn(imgs * s, c, device=DEV).half()
     nw = ops.prep_norm(torch.ones(c), torch.zeros(c), DEV)
     ms = timeit(lambda: ops.layer_norm(xin, nw, out=out))

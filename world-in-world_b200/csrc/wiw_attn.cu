@@ -16,6 +16,8 @@
 #include "wiw_common.cuh"
 #include "../../include/wiw.h"
 
+#include <cstdlib>
+
 namespace wiw {
 
 constexpr int kQ = 128, kKV = 128, kD = 64;
@@ -52,7 +54,7 @@ __device__ __forceinline__ float exp2_poly(float x) {
     const float p = fmaf(fmaf(fmaf(0.05517167f, f, 0.24261113f), f, 0.69326097f), f, 0.99992806f);
     return __int_as_float(__float_as_int(p) + (__float_as_int(xr) << 23));
 }
-constexpr int kPolyPairs = 0;                          // of every 4 (pairs of) exponentials, this many use exp2_poly
+// POLY template parameter: of every 4 (pairs of) exponentials, this many use exp2_poly (0 = all on the MUFU pipe)
 
 struct AttnArgs {
     int S, nkv;
@@ -74,6 +76,7 @@ __device__ __forceinline__ float row_max_chunk(const uint32_t* r, float mx) {
 
 // 32 scores -> 32 fp16 probabilities p = 2^(s*c - mc) written to the swizzled P tile
 // (fp32 MUFU.EX2 + one F2FP pack per pair: cheaper than ex2.f16x2, which splits into two MUFU + a PRMT)
+template <int kPolyPairs>
 __device__ __forceinline__ void exp_chunk(const uint32_t* r, int ch, float c, float mc, uint8_t* dst, uint32_t sw) {
 #pragma unroll
     for (int v8 = 0; v8 < 4; ++v8) {
@@ -90,6 +93,7 @@ __device__ __forceinline__ void exp_chunk(const uint32_t* r, int ch, float c, fl
     }
 }
 
+template <int POLY>
 __global__ void __launch_bounds__(kAttnThreads, 1)
 attn_spatial_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_out,
                     const __grid_constant__ AttnArgs a, int C) {
@@ -295,17 +299,17 @@ attn_spatial_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
                 tmem_ld_32x32b_x32(tS, ra);
                 tmem_ld_wait();
                 tmem_ld_32x32b_x32(tS + 32, rb);
-                exp_chunk(ra, 0, c, mc, pP, sw);
+                exp_chunk<POLY>(ra, 0, c, mc, pP, sw);
                 tmem_ld_wait();
                 tmem_ld_32x32b_x32(tS + 64, ra);
-                exp_chunk(rb, 1, c, mc, pP, sw);
+                exp_chunk<POLY>(rb, 1, c, mc, pP, sw);
                 tmem_ld_wait();
                 tmem_ld_32x32b_x32(tS + 96, rb);
-                exp_chunk(ra, 2, c, mc, pP + kTileBytes, sw);
+                exp_chunk<POLY>(ra, 2, c, mc, pP + kTileBytes, sw);
                 tmem_ld_wait();
                 tc_fence_before();                               // last read of S_t: release it for the next QK
                 mbar_arrive(bar_s_free + 8 * t);
-                exp_chunk(rb, 3, c, mc, pP + kTileBytes, sw);
+                exp_chunk<POLY>(rb, 3, c, mc, pP + kTileBytes, sw);
             } else {
 #pragma unroll 1
                 for (int ch = 0; ch < 4; ++ch) {
@@ -317,7 +321,7 @@ attn_spatial_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
                         mbar_arrive(bar_s_free + 8 * t);
                     }
                     mask_chunk(r, ch * 32, valid);
-                    exp_chunk(r, ch, c, mc, pP + (ch >> 1) * kTileBytes, sw);
+                    exp_chunk<POLY>(r, ch, c, mc, pP + (ch >> 1) * kTileBytes, sw);
                 }
             }
             fence_proxy_async_smem();
@@ -397,11 +401,17 @@ extern "C" int wiw_attention_spatial(const void* qkv, void* out, int images, int
     a.scale_log2 = 0.125f * 1.4426950408889634f;
     static bool attr_set = false;
     if (!attr_set) {
-        WIW_CHECK_CUDA(cudaFuncSetAttribute(attn_spatial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
+        WIW_CHECK_CUDA(cudaFuncSetAttribute(attn_spatial_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
+        WIW_CHECK_CUDA(cudaFuncSetAttribute(attn_spatial_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
+        WIW_CHECK_CUDA(cudaFuncSetAttribute(attn_spatial_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
         attr_set = true;
     }
+    // share of the exponentials evaluated on the FMA pipe instead of MUFU (development aid for A/B runs; see exp2_poly)
+    static const int poly = getenv("WIW_ATTN_POLY") ? atoi(getenv("WIW_ATTN_POLY")) : 0;
     dim3 grid((S + 2 * kQ - 1) / (2 * kQ), C / 64, images);
-    attn_spatial_kernel<<<grid, kAttnThreads, kAttnSmem, stream>>>(tm_qkv, tm_out, a, C);
+    if (poly == 1) attn_spatial_kernel<1><<<grid, kAttnThreads, kAttnSmem, stream>>>(tm_qkv, tm_out, a, C);
+    else if (poly == 2) attn_spatial_kernel<2><<<grid, kAttnThreads, kAttnSmem, stream>>>(tm_qkv, tm_out, a, C);
+    else attn_spatial_kernel<0><<<grid, kAttnThreads, kAttnSmem, stream>>>(tm_qkv, tm_out, a, C);
     WIW_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

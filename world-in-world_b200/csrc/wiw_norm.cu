@@ -657,14 +657,18 @@ extern "C" int wiw_layernorm(const void* x, void* y, long long M, int C, const f
     const int nvec = C / 8;
     static const int norm_v = getenv("WIW_NORM_V") ? atoi(getenv("WIW_NORM_V")) : 2;          // development aid for A/B runs
     if (norm_v >= 2) {
+        static bool attr_set = false;
+        if (!attr_set) {            // (all instantiations share one function-pointer type: set each explicitly)
+            WIW_CHECK_CUDA(cudaFuncSetAttribute(layernorm_stream_kernel<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+            WIW_CHECK_CUDA(cudaFuncSetAttribute(layernorm_stream_kernel<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+            WIW_CHECK_CUDA(cudaFuncSetAttribute(layernorm_stream_kernel<3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+            WIW_CHECK_CUDA(cudaFuncSetAttribute(layernorm_stream_kernel<5, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+            WIW_CHECK_CUDA(cudaFuncSetAttribute(layernorm_stream_kernel<8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+            attr_set = true;
+        }
         auto launch = [&](auto kern, int rpw) -> int {
             const int tile_rows = 8 * rpw;
             const size_t smem = (size_t)kRing * tile_rows * C * 2 + 128;
-            static bool attr_set = false;                                     // one flag per kernel instantiation (generic lambda)
-            if (!attr_set) {
-                WIW_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-                attr_set = true;
-            }
             WIW_REQUIRE(smem <= 160 * 1024, "LayerNorm tile does not fit shared memory");
             long long rows_per_cta = (M + 2 * num_sms() - 1) / (2 * num_sms());
             rows_per_cta = (rows_per_cta + tile_rows - 1) / tile_rows * tile_rows;

@@ -144,7 +144,9 @@ def _launch(a: torch.Tensor, a_dim, a_stride, gw: GemmWeight, out: torch.Tensor,
     L.check(lib.wiw_conv_gemm(d, L.stream_ptr()))
     e1.record()
     rows = int(out_dim[1]) * int(out_dim[2]) * int(out_dim[3])
-    PROFILE.append((2.0 * rows * (gw.n_real or gw.n) * (gw.k_real or gw.k), e0, e1))
+    PROFILE.append((2.0 * rows * (gw.n_real or gw.n) * (gw.k_real or gw.k), e0, e1,
+                    f"M={rows} K={gw.k} N={gw.n} taps={len(taps)} bn={gw.bn}{' geglu' if gw.geglu else ''}"
+                    f"{' res' if res is not None else ''}{' aux' if aux is not None else ''}{' tab' if tab is not None else ''}"))
 
 
 def _chk(x: torch.Tensor) -> None:
