@@ -26,6 +26,7 @@ def timeit(fn, iters=5):
     return ts[len(ts) // 2]
 
 
+ONLY = sys.argv[1] if len(sys.argv) > 1 else ""
 rows = []
 def rec(name, ms, flop):
     rows.append({"name": name, "ms": round(ms, 4), "tflops": round(flop / ms / 1e9, 1)})
@@ -34,9 +35,13 @@ def rec(name, ms, flop):
 for (m, c) in [(258048, 320), (64512, 640), (16128, 1280)]:
     x = torch.randn(m, c, device=DEV).half()
     for (name, n, geglu) in [("qkv", 3 * c, False), ("proj", c, False), ("ff1_geglu", 8 * c, True)]:
+        if ONLY and ONLY not in name:
+            continue
         gw = ops.prep_linear(torch.randn(n, c) * c ** -0.5, torch.randn(n), DEV, geglu=geglu)
         out = torch.empty(m, gw.n // 2 if geglu else gw.n, device=DEV, dtype=torch.half)
         rec(f"linear {name} M={m} K={c} N={n} bn={gw.bn}", timeit(lambda: ops.linear(x, gw, out=out)), 2.0 * m * c * n)
+    if ONLY:
+        continue
     x4 = torch.randn(m, 4 * c, device=DEV).half()
     res = torch.randn(m, c, device=DEV).half()
     gw = ops.prep_linear(torch.randn(c, 4 * c) * (4 * c) ** -0.5, torch.randn(c), DEV)
@@ -44,6 +49,8 @@ for (m, c) in [(258048, 320), (64512, 640), (16128, 1280)]:
     rec(f"linear ff2+res M={m} K={4*c} N={c} bn={gw.bn}", timeit(lambda: ops.linear(x4, gw, res=res, out=out)), 2.0 * m * 4 * c * c)
     del x4, res
 
+if ONLY:
+    sys.exit(0)
 for (n, h, w, cin, cout) in [(28, 72, 128, 320, 320), (28, 36, 64, 640, 640), (28, 18, 32, 1280, 1280), (28, 72, 128, 960, 320)]:
     x = torch.randn(n, h, w, cin, device=DEV).half()
     gw = ops.prep_conv(torch.randn(cout, cin, 3, 3) * (9 * cin) ** -0.5, torch.randn(cout), DEV)

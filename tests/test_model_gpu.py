@@ -83,6 +83,8 @@ def test_unet_forward_vs_golden_and_oracle(golden_dir, unet, unet_sd):
         r = torch.from_numpy(g["tap." + k])
         assert rel_rms(got, r) < 1e-2, f"tap {k}: rel rms {rel_rms(got, r):.4g}"
     assert torch.isfinite(out).all()
+    from conftest import record_parity
+    record_parity("tiny_unet_forward_vs_golden", rel_rms=rel_rms(out, ref), psnr_db=psnr_range(out, ref))
     assert rel_rms(out, ref) < 1e-2, f"unet out rel rms {rel_rms(out, ref):.4g}"
     assert psnr_range(out, ref) > 45.0
     # and against the oracle evaluated on the fp16-rounded inputs (what the kernels actually saw)
@@ -130,6 +132,8 @@ def test_rollout_vs_reference_pipeline(golden_dir, unet, vae):
     p = O.psnr(frames, g["frames"][0])
     assert p >= 45.0, f"frame PSNR {p:.2f} dB < 45"
     p8 = O.psnr(u8.cpu().numpy().astype(np.float32) / 255.0, g["frames"][0])
+    from conftest import record_parity
+    record_parity("tiny_rollout_vs_reference_pipeline", latents_psnr_db=psnr_range(final, ref_lat), frames_psnr_db=p, frames_u8_psnr_db=p8)
     assert p8 >= 45.0, f"uint8 frame PSNR {p8:.2f} dB < 45"
 
 

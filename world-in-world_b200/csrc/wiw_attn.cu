@@ -407,7 +407,7 @@ extern "C" int wiw_attention_spatial(const void* qkv, void* out, int images, int
         attr_set = true;
     }
     // share of the exponentials evaluated on the FMA pipe instead of MUFU (development aid for A/B runs; see exp2_poly)
-    static const int poly = getenv("WIW_ATTN_POLY") ? atoi(getenv("WIW_ATTN_POLY")) : 0;
+    static const int poly = getenv("WIW_ATTN_POLY") ? atoi(getenv("WIW_ATTN_POLY")) : 1;       // A/B on B200: 1 of 4 pairs on the FMA pipe = +6 % at S=9216; 2 of 4 = -4 %
     dim3 grid((S + 2 * kQ - 1) / (2 * kQ), C / 64, images);
     if (poly == 1) attn_spatial_kernel<1><<<grid, kAttnThreads, kAttnSmem, stream>>>(tm_qkv, tm_out, a, C);
     else if (poly == 2) attn_spatial_kernel<2><<<grid, kAttnThreads, kAttnSmem, stream>>>(tm_qkv, tm_out, a, C);

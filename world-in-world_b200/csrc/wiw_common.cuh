@@ -298,6 +298,21 @@ __device__ __forceinline__ float gelu_fast_f(float x) {
     const float qh = 0.5f * poly * t * e;
     return x >= 0.f ? fmaf(-x, qh, x) : x * qh;
 }
+// v * gelu(x) with the exact-erf GELU evaluated through ONE MUFU op:
+//   Phi(x) = 0.5 (1 + tanh(x (c0 + c1 x^2 + c2 x^4))),  odd polynomial fitted to atanh(erf(x / sqrt 2)) on |x| <= 6
+// Formula error |Phi - Phi_exact| <= 5.8e-5, |gelu - gelu_exact| <= 3.0e-5 (16x closer to erf-GELU than the classic
+// "tanh GELU" constants); MUFU.TANH adds <= 2^-11 relative on tanh, i.e. <= 2.4e-4 |x| on gelu -- half an fp16 ulp of the
+// fp16 hidden tile this value is rounded to.  7 FMA-pipe instructions + 1 MUFU per element instead of 13 + 2
+// (gelu_fast_f): the GEGLU epilogue of the K = 320 MLPs is issue- and MUFU-bound, not tensor-bound (profiles/r01_ncu_full_v5.md).
+__device__ __forceinline__ float mul_gelu_tanhfit_f(float v, float x) {
+    const float x2 = x * x;
+    float p = fmaf(x2, -3.58549415e-4f, 3.70488970e-2f);
+    p = fmaf(p, x2, 7.97460674e-1f);
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(x * p));
+    const float w = v * (0.5f * x);
+    return fmaf(w, t, w);
+}
 #endif  // __CUDACC__
 
 }  // namespace wiw

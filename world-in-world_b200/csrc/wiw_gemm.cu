@@ -70,7 +70,7 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmArgs& g, int tile, in
     return t;
 }
 
-template <int CG, bool GEGLU>
+template <int CG, int GEGLU>      // GEGLU: 0 = plain epilogue, 1 = GEGLU with the A&S erf (gelu_fast_f), 2 = GEGLU with the tanh-fit erf
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                  const __grid_constant__ CUtensorMap tm_out /* box = one warp's 32 rows x 32 channels */,
@@ -348,10 +348,17 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                     tmem_ld_wait();
 #pragma unroll
                     for (int c = 0; c < kEpiCols; c += 4) {
-                        v[c] *= gelu_fast_f(__uint_as_float(rg[c]) + b4[c / 4].x);
-                        v[c + 1] *= gelu_fast_f(__uint_as_float(rg[c + 1]) + b4[c / 4].y);
-                        v[c + 2] *= gelu_fast_f(__uint_as_float(rg[c + 2]) + b4[c / 4].z);
-                        v[c + 3] *= gelu_fast_f(__uint_as_float(rg[c + 3]) + b4[c / 4].w);
+                        if (GEGLU == 2) {
+                            v[c] = mul_gelu_tanhfit_f(v[c], __uint_as_float(rg[c]) + b4[c / 4].x);
+                            v[c + 1] = mul_gelu_tanhfit_f(v[c + 1], __uint_as_float(rg[c + 1]) + b4[c / 4].y);
+                            v[c + 2] = mul_gelu_tanhfit_f(v[c + 2], __uint_as_float(rg[c + 2]) + b4[c / 4].z);
+                            v[c + 3] = mul_gelu_tanhfit_f(v[c + 3], __uint_as_float(rg[c + 3]) + b4[c / 4].w);
+                        } else {
+                            v[c] *= gelu_fast_f(__uint_as_float(rg[c]) + b4[c / 4].x);
+                            v[c + 1] *= gelu_fast_f(__uint_as_float(rg[c + 1]) + b4[c / 4].y);
+                            v[c + 2] *= gelu_fast_f(__uint_as_float(rg[c + 2]) + b4[c / 4].z);
+                            v[c + 3] *= gelu_fast_f(__uint_as_float(rg[c + 3]) + b4[c / 4].w);
+                        }
                     }
                 }
                 if (j == last_j) {
@@ -496,6 +503,7 @@ static int launch_conv_gemm(const wiw_gemm_desc* d, cudaStream_t stream) {
     g.total_tiles = (int)(((m_tiles + cg - 1) / cg) * g.n_tiles);
     static const int dbg = getenv("WIW_GEMM_DBG") ? atoi(getenv("WIW_GEMM_DBG")) : 0;
     g.dbg = dbg;
+    static const int gelu_mode = getenv("WIW_GELU") ? atoi(getenv("WIW_GELU")) : 2;         // 1 = A&S erf (2 MUFU), 2 = tanh-fit erf (1 MUFU)
     static const int epi = getenv("WIW_GEMM_EPI") ? atoi(getenv("WIW_GEMM_EPI")) : 1;       // development aid for A/B runs
     g.warp_store = epi ? 1 : 0;
     const int sbx = d->bx < 32 ? d->bx : 32, sby = 32 / sbx;                                // one warp's 32 rows as a pixel box
@@ -553,17 +561,20 @@ static int launch_conv_gemm(const wiw_gemm_desc* d, cudaStream_t stream) {
 
     static bool attr_set = false;
     if (!attr_set) {
-        WIW_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
-        WIW_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
-        WIW_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
-        WIW_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+        WIW_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+        WIW_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+        WIW_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+        WIW_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+        WIW_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+        WIW_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
         attr_set = true;
     }
     if (cg == 1) {
         int grid = num_sms();
         if (grid > g.total_tiles) grid = g.total_tiles;
-        if (g.geglu) conv_gemm_kernel<1, true><<<grid, kThreads, smem_bytes, stream>>>(tm_a, tm_b, tm_out, tm_res, tm_aux, g);
-        else conv_gemm_kernel<1, false><<<grid, kThreads, smem_bytes, stream>>>(tm_a, tm_b, tm_out, tm_res, tm_aux, g);
+        if (g.geglu && gelu_mode == 2) conv_gemm_kernel<1, 2><<<grid, kThreads, smem_bytes, stream>>>(tm_a, tm_b, tm_out, tm_res, tm_aux, g);
+        else if (g.geglu) conv_gemm_kernel<1, 1><<<grid, kThreads, smem_bytes, stream>>>(tm_a, tm_b, tm_out, tm_res, tm_aux, g);
+        else conv_gemm_kernel<1, 0><<<grid, kThreads, smem_bytes, stream>>>(tm_a, tm_b, tm_out, tm_res, tm_aux, g);
     } else {
         int pairs = num_sms() / 2;
         if (pairs > g.total_tiles) pairs = g.total_tiles;
@@ -578,8 +589,9 @@ static int launch_conv_gemm(const wiw_gemm_desc* d, cudaStream_t stream) {
         attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        if (g.geglu) WIW_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<2, true>, tm_a, tm_b, tm_out, tm_res, tm_aux, g));
-        else WIW_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<2, false>, tm_a, tm_b, tm_out, tm_res, tm_aux, g));
+        if (g.geglu && gelu_mode == 2) WIW_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<2, 2>, tm_a, tm_b, tm_out, tm_res, tm_aux, g));
+        else if (g.geglu) WIW_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<2, 1>, tm_a, tm_b, tm_out, tm_res, tm_aux, g));
+        else WIW_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<2, 0>, tm_a, tm_b, tm_out, tm_res, tm_aux, g));
     }
     WIW_CHECK_CUDA(cudaGetLastError());
     return 0;

@@ -348,9 +348,6 @@ layernorm_stream_kernel(const __half* __restrict__ x, __half* __restrict__ y, co
                                                      : make_uint4(0, 0, 0, 0);
             }
         }
-        // every lane has its copy of the tile's rows: hand the stage back before the arithmetic
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_empty + 8 * s);
 #pragma unroll
         for (int k = 0; k < RPW; ++k) {
             const int lr = warp + 8 * k;
@@ -416,6 +413,10 @@ layernorm_stream_kernel(const __half* __restrict__ x, __half* __restrict__ y, co
                 }
             }
         }
+        // Release the stage only after the loaded registers were consumed: an LDS is complete once its destination has
+        // been read, not when it was issued (an arrive right after issuing the loads raced with the next TMA write).
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_empty + 8 * s);
         if (++s == kRing) { s = 0; ph ^= 1; }
     }
 }
@@ -465,10 +466,10 @@ gn_stats_stream_kernel(const __half* __restrict__ x, float* __restrict__ partial
                 const int lr = k * RL + rl;
                 u[k] = (active && lr < rows) ? *reinterpret_cast<const uint4*>(tile + (size_t)lr * row_bytes + v * 16) : make_uint4(0, 0, 0, 0);
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_empty + 8 * st);
 #pragma unroll
             for (int k = 0; k < kGnKU; ++k) acc8(u[k], s, q);          // padded rows add zeros
+            __syncwarp();                                              // loads consumed -> the stage may be overwritten
+            if (lane == 0) mbar_arrive(bar_empty + 8 * st);
             if (++st == kRing) { st = 0; ph ^= 1; }
         }
         if (active) {
@@ -548,13 +549,13 @@ gn_apply_stream_kernel(const __half* __restrict__ x, __half* __restrict__ y, con
             const int lr = k * RL + rl;
             u[k] = (active && lr < rows) ? *reinterpret_cast<const uint4*>(tile + (size_t)lr * row_bytes + v * 16) : make_uint4(0, 0, 0, 0);
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_empty + 8 * st);
 #pragma unroll
         for (int k = 0; k < kGnKU; ++k) {
             const int lr = k * RL + rl;
             if (active && lr < rows) *reinterpret_cast<uint4*>(y + (row_base + r + lr) * C + v * 8) = gn_apply8(u[k], sc, sh, silu);
         }
+        __syncwarp();                                                  // loads consumed -> the stage may be overwritten
+        if (lane == 0) mbar_arrive(bar_empty + 8 * st);
         if (++st == kRing) { st = 0; ph ^= 1; }
     }
 }
@@ -579,7 +580,7 @@ extern "C" int wiw_groupnorm(const void* x, void* y, int samples, long long rows
     WIW_REQUIRE(threads <= 1024, "C too large");
     float* partial = workspace;
     float* stats = workspace + (size_t)samples * kGnMaxChunks * G * 2;
-    static const int norm_v = getenv("WIW_NORM_V") ? atoi(getenv("WIW_NORM_V")) : 2;          // development aid for A/B runs
+    static const int norm_v = getenv("WIW_NORM_V") ? atoi(getenv("WIW_NORM_V")) : 1;          // 2 = TMA-ring streaming variants (A/B: no faster)
     const double count = (double)rows_per_sample * (C / G);
     if (norm_v >= 2 && vpr <= 256) {
         // streaming kernels: (chunk, sample) CTAs of contiguous rows, ~2-3 CTAs per SM, 4-stage TMA ring each
@@ -655,7 +656,7 @@ extern "C" int wiw_layernorm(const void* x, void* y, long long M, int C, const f
     const __half* xi = static_cast<const __half*>(x);
     __half* yo = static_cast<__half*>(y);
     const int nvec = C / 8;
-    static const int norm_v = getenv("WIW_NORM_V") ? atoi(getenv("WIW_NORM_V")) : 2;          // development aid for A/B runs
+    static const int norm_v = getenv("WIW_NORM_V") ? atoi(getenv("WIW_NORM_V")) : 1;          // 2 = TMA-ring streaming variants (A/B: no faster)
     if (norm_v >= 2) {
         static bool attr_set = false;
         if (!attr_set) {            // (all instantiations share one function-pointer type: set each explicitly)
