@@ -25,7 +25,7 @@ constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;                    // 64 fp16 = one 128-byte swizzle row
 constexpr int kEpiCols = 32;                   // epilogue chunk: 32 fp16 = 64-byte rows (SWIZZLE_64B)
 constexpr int kEpiChunkBytes = kBlockM * kEpiCols * 2;   // 8 KB
-constexpr int kOutBufs = 4;                    // 2 per epilogue group
+constexpr int kMaxOutBufs = 8;                 // staging chunks: 2 or 4 per epilogue group (GemmArgs::out_bufs)
 constexpr int kResSlots = 4;
 constexpr int kMaxStages = 8;
 constexpr int kThreads = 11 * 32;              // TMA, MMA, epilogue loader, 2 x 4 epilogue warps
@@ -39,6 +39,7 @@ struct GemmArgs {
     int tab_div, tab_mod, n_total, tmem_cols;
     int tab_stride, act, out_total;
     int dbg;                                      // development aid: bit 0 = skip TMA loads, bit 1 = skip MMA issue (timing only)
+    int out_bufs;                                 // staging buffers per epilogue group: 4 when no residual / aux slots compete for smem, else 2
     int warp_store;                               // 1: every epilogue warp stores its own 32-row slab (no CTA barriers); 0: one store per 128-row chunk
     int wx0[4], wy0[4];                           // pixel offset of epilogue warp q's 32 rows inside the bx x by tile
     const float* bias;
@@ -83,7 +84,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     const uint32_t b_bytes = (g.bn / CG) * kBlockK * 2;          // with cta_group::2 each CTA stages half of the N-tile
     const uint32_t stage_bytes = a_bytes + b_bytes;
     const uint32_t out_base = smem_base + g.stages * stage_bytes;
-    const uint32_t res_base = out_base + kOutBufs * kEpiChunkBytes;
+    const uint32_t res_base = out_base + 2 * g.out_bufs * kEpiChunkBytes;
     const uint32_t aux_base = res_base + (g.has_res ? kResSlots * kEpiChunkBytes : 0);
     const uint32_t bar_base = aux_base + (g.has_aux ? kResSlots * kEpiChunkBytes : 0);
     // barrier slots (8 B each)
@@ -263,7 +264,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         const uint32_t bar_id = 1 + grp;
         int as = 0;
         uint32_t aph = 0;
-        int ob = 0;                                    // this group's staging buffer (2 per group)
+        int ob = 0;                                    // this group's staging buffer (g.out_bufs per group, round robin)
+        const int nob = g.out_bufs;
         long long chunk_base = 0;                      // chunks consumed by this CTA before the current tile
         int chunks = 0;
         const bool eprof = (g.dbg & 4) && blockIdx.x == 0 && warp == 3;
@@ -409,15 +411,16 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 }
                 // The store issued two chunks ago by this group read the buffer we are about to overwrite:
                 // the leader waits until at most one of its bulk groups is still reading, then releases the group.
+                // the store issued `nob` chunks ago read the buffer about to be overwritten
                 if (g.warp_store) {
-                    if (elect_one()) tma_store_wait_read<1>();
+                    if (elect_one()) { if (nob == 4) tma_store_wait_read<3>(); else tma_store_wait_read<1>(); }
                     __syncwarp();
                 } else {
-                    if (store_warp) { if (elect_one()) tma_store_wait_read<1>(); __syncwarp(); }
+                    if (store_warp) { if (elect_one()) { if (nob == 4) tma_store_wait_read<3>(); else tma_store_wait_read<1>(); } __syncwarp(); }
                     asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
                 }
                 {
-                    uint8_t* p = smem_raw + (out_base - smem_u32(smem_raw)) + (grp * 2 + ob) * kEpiChunkBytes + row_off;
+                    uint8_t* p = smem_raw + (out_base - smem_u32(smem_raw)) + (grp * nob + ob) * kEpiChunkBytes + row_off;
 #pragma unroll
                     for (int c4 = 0; c4 < 4; ++c4) {
                         uint4 u;
@@ -431,7 +434,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 if (g.warp_store) {
                     __syncwarp();                                  // the slab is complete and visible to the async proxy
                     if (elect_one()) {
-                        tma_store_4d(&tm_out, out_base + (grp * 2 + ob) * kEpiChunkBytes + q * (32 * 64), out_c0 + j * kEpiCols,
+                        tma_store_4d(&tm_out, out_base + (grp * nob + ob) * kEpiChunkBytes + q * (32 * 64), out_c0 + j * kEpiCols,
                                      t.x0 + g.wx0[q], t.y0 + g.wy0[q], t.img);
                         tma_store_commit();
                     }
@@ -440,13 +443,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                     asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
                     if (store_warp) {
                         if (elect_one()) {
-                            tma_store_4d(&tm_out, out_base + (grp * 2 + ob) * kEpiChunkBytes, out_c0 + j * kEpiCols, t.x0, t.y0, t.img);
+                            tma_store_4d(&tm_out, out_base + (grp * nob + ob) * kEpiChunkBytes, out_c0 + j * kEpiCols, t.x0, t.y0, t.img);
                             tma_store_commit();
                         }
                         __syncwarp();
                     }
                 }
-                ob ^= 1;
+                if (++ob == nob) ob = 0;
             }
             if (++as == 2) { as = 0; aph ^= 1; }
         }
@@ -525,7 +528,9 @@ static int launch_conv_gemm(const wiw_gemm_desc* d, cudaStream_t stream) {
     if (cg == 2) g.tmem_cols = 512;   // pair allocations always take the whole TMEM (as CUTLASS does): both CTAs must see the same base
 
     const int stage_bytes = kBlockM * kBlockK * 2 + (g.bn / cg) * kBlockK * 2;
-    const int fixed = 1024 /*align slack*/ + kOutBufs * kEpiChunkBytes + (g.has_res ? kResSlots * kEpiChunkBytes : 0) +
+    static const int obufs_env = getenv("WIW_GEMM_OBUFS") ? atoi(getenv("WIW_GEMM_OBUFS")) : 4;   // development aid for A/B runs
+    g.out_bufs = (!g.has_res && !g.has_aux && obufs_env == 4) ? 4 : 2;
+    const int fixed = 1024 /*align slack*/ + 2 * g.out_bufs * kEpiChunkBytes + (g.has_res ? kResSlots * kEpiChunkBytes : 0) +
                       (g.has_aux ? kResSlots * kEpiChunkBytes : 0) + 256 /*barriers*/;
     int stages = (kSmemBudget - fixed) / stage_bytes;
     if (stages > kMaxStages) stages = kMaxStages;

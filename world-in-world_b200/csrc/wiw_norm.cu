@@ -246,6 +246,114 @@ __global__ void layernorm_kernel(const __half* __restrict__ x, __half* __restric
 }
 
 
+// ---------------------------------------------------------------- LayerNorm, lane-group variant (default)
+// ncu of layernorm_kernel<2,4> at C = 320 (profiles/r01_ncu_norm_v7.md): 255 warp-instructions per row, 64 % issue
+// utilisation, 9x L1 load amplification (gamma / beta re-read per row, second vector 25 % full) at 37 % of DRAM peak.
+// Here LPR lanes share a row so every lane owns VPL full vectors (C = 320: 8 lanes x 5 vectors, 4 rows per warp),
+// gamma / beta sit in registers as packed halves for the warp's whole life, statistics are single-pass fp32 sums
+// (sum, sum of squares) reduced over the LPR lanes, and the next row group's loads are issued before the current
+// group's arithmetic.  ~80 warp-instructions per row.
+template <int LPR, int VPL>
+__global__ void __launch_bounds__(256, 2)
+layernorm_lpr_kernel(const __half* __restrict__ x, __half* __restrict__ y, const float* __restrict__ gamma,
+                     const float* __restrict__ beta, const __half* __restrict__ tab, int tab_div, int tab_mod,
+                     long long M, int C, float eps, int groups_per_warp) {
+    constexpr int RPW = 32 / LPR;                       // rows per warp per group
+    const int lane = threadIdx.x & 31;
+    const int sub = lane / LPR, j = lane % LPR;
+    const int nvec = C >> 3;
+    const long long warp_global = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long long g0 = warp_global * groups_per_warp;
+    if (g0 * RPW >= M) return;
+    uint32_t gpk[VPL][4], bpk[VPL][4];                  // gamma / beta of this lane's channels as half2
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+        const int vi = j + LPR * i;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float2 gv = (vi < nvec) ? *reinterpret_cast<const float2*>(gamma + vi * 8 + 2 * e) : make_float2(0.f, 0.f);
+            const float2 bv = (vi < nvec) ? *reinterpret_cast<const float2*>(beta + vi * 8 + 2 * e) : make_float2(0.f, 0.f);
+            const __half2 gh = __floats2half2_rn(gv.x, gv.y), bh = __floats2half2_rn(bv.x, bv.y);
+            gpk[i][e] = *reinterpret_cast<const uint32_t*>(&gh);
+            bpk[i][e] = *reinterpret_cast<const uint32_t*>(&bh);
+        }
+    }
+    const float inv_c = 1.0f / (float)C;
+    auto load_group = [&](long long g, uint4* raw) {
+        const long long row = g * RPW + sub;
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) {
+            const int vi = j + LPR * i;
+            raw[i] = (vi < nvec && row < M) ? __ldg(reinterpret_cast<const uint4*>(x + row * C + vi * 8)) : make_uint4(0, 0, 0, 0);
+        }
+    };
+    uint4 cur[VPL], nxt[VPL];
+    load_group(g0, cur);
+    for (int gi = 0; gi < groups_per_warp; ++gi) {
+        const long long g = g0 + gi;
+        if (g * RPW >= M) break;                        // warp-uniform
+        if (gi + 1 < groups_per_warp) load_group(g + 1, nxt);
+        const long long row = g * RPW + sub;
+        if (tab != nullptr && row < M) {                // the reference adds the embedding in fp16 (transformer_temporal.py:360)
+            const __half* trow = tab + (size_t)((row / tab_div) % tab_mod) * C;
+#pragma unroll
+            for (int i = 0; i < VPL; ++i) {
+                const int vi = j + LPR * i;
+                if (vi < nvec) {
+                    const uint4 tu = __ldg(reinterpret_cast<const uint4*>(trow + vi * 8));
+                    __half2* h = reinterpret_cast<__half2*>(&cur[i]);
+                    const __half2* th = reinterpret_cast<const __half2*>(&tu);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) h[e] = __hadd2(h[e], th[e]);
+                }
+            }
+        }
+        float sum = 0.f, sq = 0.f;
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) {
+            const __half2* h = reinterpret_cast<const __half2*>(&cur[i]);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float2 f = __half22float2(h[e]);
+                sum += f.x; sq = fmaf(f.x, f.x, sq);
+                sum += f.y; sq = fmaf(f.y, f.y, sq);
+            }
+        }
+#pragma unroll
+        for (int o = LPR / 2; o > 0; o >>= 1) {
+            sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            sq += __shfl_xor_sync(0xffffffffu, sq, o);
+        }
+        const float mean = sum * inv_c;
+        float var = fmaf(-mean, mean, sq * inv_c);
+        var = var < 0.f ? 0.f : var;
+        const float rstd = rsqrtf(var + eps);
+        const float nmr = -mean * rstd;
+        if (row < M) {
+#pragma unroll
+            for (int i = 0; i < VPL; ++i) {
+                const int vi = j + LPR * i;
+                if (vi < nvec) {
+                    const __half2* h = reinterpret_cast<const __half2*>(&cur[i]);
+                    uint4 o;
+                    __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        // normalise in fp32, affine as one packed fp16 FMA (gamma / beta stay packed: no loop-invariant
+                        // unpacking for the compiler to hoist into 80 more registers)
+                        const float2 f = __half22float2(h[e]);
+                        const __half2 t = __floats2half2_rn(fmaf(f.x, rstd, nmr), fmaf(f.y, rstd, nmr));
+                        oh[e] = __hfma2(t, *reinterpret_cast<const __half2*>(&gpk[i][e]), *reinterpret_cast<const __half2*>(&bpk[i][e]));
+                    }
+                    *reinterpret_cast<uint4*>(y + row * C + vi * 8) = o;
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) cur[i] = nxt[i];
+    }
+}
+
 // ================================================================================================
 // TMA-fed streaming variants (default).  The register-staged kernels above keep only
 // (threads x unroll x 16 B) in flight and stop loading while they compute, which holds them at ~45 % of the HBM
@@ -656,8 +764,35 @@ extern "C" int wiw_layernorm(const void* x, void* y, long long M, int C, const f
     const __half* xi = static_cast<const __half*>(x);
     __half* yo = static_cast<__half*>(y);
     const int nvec = C / 8;
-    static const int norm_v = getenv("WIW_NORM_V") ? atoi(getenv("WIW_NORM_V")) : 1;          // 2 = TMA-ring streaming variants (A/B: no faster)
-    if (norm_v >= 2) {
+    static const int norm_v = getenv("WIW_NORM_V") ? atoi(getenv("WIW_NORM_V")) : 3;          // 3 = lane-group kernel (default), 1 = one warp per row, 2 = TMA-ring streaming
+    if (norm_v == 3) {
+        auto launch = [&](auto kern, int lpr) -> int {
+            const int rpw = 32 / lpr;
+            const long long groups = (M + rpw - 1) / rpw;
+            // enough warps for ~4 waves of 16 warps per SM, at most 8 row groups per warp
+            long long gpw = groups / ((long long)num_sms() * 16 * 4);
+            if (gpw < 1) gpw = 1;
+            if (gpw > 8) gpw = 8;
+            const long long warps = (groups + gpw - 1) / gpw;
+            const unsigned grid = (unsigned)((warps + 7) / 8);
+            kern<<<grid, 256, 0, stream>>>(xi, yo, gamma, beta, tab, tab_div, tab_mod, M, C, eps, (int)gpw);
+            WIW_CHECK_CUDA(cudaGetLastError());
+            return 0;
+        };
+        if (nvec <= 8) return launch(layernorm_lpr_kernel<8, 1>, 8);
+        if (nvec <= 16) return launch(layernorm_lpr_kernel<8, 2>, 8);
+        if (nvec <= 24) return launch(layernorm_lpr_kernel<8, 3>, 8);
+        if (nvec <= 32) return launch(layernorm_lpr_kernel<8, 4>, 8);
+        if (nvec <= 40) return launch(layernorm_lpr_kernel<8, 5>, 8);
+        if (nvec <= 48) return launch(layernorm_lpr_kernel<16, 3>, 16);
+        if (nvec <= 64) return launch(layernorm_lpr_kernel<16, 4>, 16);
+        if (nvec <= 80) return launch(layernorm_lpr_kernel<16, 5>, 16);
+        if (nvec <= 96) return launch(layernorm_lpr_kernel<32, 3>, 32);
+        if (nvec <= 128) return launch(layernorm_lpr_kernel<32, 4>, 32);
+        if (nvec <= 160) return launch(layernorm_lpr_kernel<32, 5>, 32);
+        // wider rows: fall through to the one-warp-per-row kernel
+    }
+    if (norm_v == 2) {
         static bool attr_set = false;
         if (!attr_set) {            // (all instantiations share one function-pointer type: set each explicitly)
             WIW_CHECK_CUDA(cudaFuncSetAttribute(layernorm_stream_kernel<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
