@@ -71,7 +71,7 @@ typedef struct {
     int32_t tab_div;
     int32_t tab_mod;
     float s_acc, s_res, s_aux;
-    int32_t bx, by;         /* M-tile = by rows of bx pixels, bx*by == 128 */
+    int32_t bx, by;         /* M-tile = bz images x by rows x bx pixels, bx*by*bz == 128 (bz: last field) */
     int32_t bn;             /* N-tile, multiple of 32 (64 if geglu), <= 256 */
     int32_t geglu;
     int32_t num_taps;       /* <= 9 */
@@ -82,6 +82,7 @@ typedef struct {
     int32_t tap_oy[9];
     int32_t tab_stride;     /* row stride of tab in elements (0 = n_total) */
     int32_t act;            /* 0 none, 1 SiLU applied to (acc + bias + tab) */
+    int32_t bz;             /* images per M-tile (0 or 1 = one image): lets 9-row / 18-row feature maps fill their tiles */
 } wiw_gemm_desc;
 
 int wiw_conv_gemm(const wiw_gemm_desc* d, wiw_stream_t stream);

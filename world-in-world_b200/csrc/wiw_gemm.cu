@@ -33,7 +33,7 @@ constexpr int kSmemBudget = 227 * 1024;
 
 struct GemmArgs {
     int total_tiles, n_tiles, tiles_x, tiles_y;   // total_tiles counts PAIR tiles when cta_group == 2
-    int bx, by, dim_x, dim_y;
+    int bx, by, bz, dim_x, dim_y;                 // M-tile = bz images x by rows x bx pixels (bx*by*bz == 128)
     int bn, stages, num_taps, chunks_per_tap;
     int out_cols_per_tile, geglu, has_res, has_aux;
     int tab_div, tab_mod, n_total, tmem_cols;
@@ -41,7 +41,7 @@ struct GemmArgs {
     int dbg;                                      // development aid: bit 0 = skip TMA loads, bit 1 = skip MMA issue (timing only)
     int out_bufs;                                 // staging buffers per epilogue group: 4 when no residual / aux slots compete for smem, else 2
     int warp_store;                               // 1: every epilogue warp stores its own 32-row slab (no CTA barriers); 0: one store per 128-row chunk
-    int wx0[4], wy0[4];                           // pixel offset of epilogue warp q's 32 rows inside the bx x by tile
+    int wx0[4], wy0[4], wz0[4];                   // (pixel, row, image) offset of epilogue warp q's 32 rows inside the M-tile
     const float* bias;
     const __half* tab;
     float s_acc, s_res, s_aux;
@@ -65,7 +65,7 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmArgs& g, int tile, in
     int tx = m_tile % g.tiles_x;
     int r = m_tile / g.tiles_x;
     int ty = r % g.tiles_y;
-    t.img = r / g.tiles_y;
+    t.img = (r / g.tiles_y) * g.bz;
     t.x0 = tx * g.bx;
     t.y0 = ty * g.by;
     return t;
@@ -278,8 +278,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             chunks = min(full_chunks, (g.out_total - out_c0) / kEpiCols);      // ragged last N-tile: padded columns are skipped
             const __half* tab_row = nullptr;
             if (g.tab != nullptr) {
-                const int x = t.x0 + (row % g.bx), y = t.y0 + (row / g.bx);
-                long long grow = ((long long)t.img * g.dim_y + y) * g.dim_x + x;
+                const int x = t.x0 + (row % g.bx), y = t.y0 + (row / g.bx) % g.by, z = t.img + row / (g.bx * g.by);
+                long long grow = ((long long)z * g.dim_y + y) * g.dim_x + x;
                 if (grow < 0) grow = 0;
                 int gi = int((grow / g.tab_div) % g.tab_mod);
                 tab_row = g.tab + (size_t)gi * g.tab_stride;
@@ -435,7 +435,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                     __syncwarp();                                  // the slab is complete and visible to the async proxy
                     if (elect_one()) {
                         tma_store_4d(&tm_out, out_base + (grp * nob + ob) * kEpiChunkBytes + q * (32 * 64), out_c0 + j * kEpiCols,
-                                     t.x0 + g.wx0[q], t.y0 + g.wy0[q], t.img);
+                                     t.x0 + g.wx0[q], t.y0 + g.wy0[q], t.img + g.wz0[q]);
                         tma_store_commit();
                     }
                     __syncwarp();
@@ -470,7 +470,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 static int launch_conv_gemm(const wiw_gemm_desc* d, cudaStream_t stream) {
     WIW_REQUIRE(d != nullptr && d->a && d->w && d->out, "null pointer");
     WIW_REQUIRE(d->a_stride[0] == 1 && d->out_stride[0] == 1, "channel axis must be contiguous");
-    WIW_REQUIRE(d->bx > 0 && d->by > 0 && d->bx * d->by == kBlockM, "bx*by must be 128");
+    const int bz = d->bz > 0 ? d->bz : 1;                 // images per M-tile (0 = 1: descriptors written before the field existed)
+    WIW_REQUIRE(d->bx > 0 && d->by > 0 && d->bx * d->by * bz == kBlockM, "bx*by*bz must be 128");
     WIW_REQUIRE(d->bn >= 32 && d->bn <= 256 && d->bn % 32 == 0, "bn must be a multiple of 32 in [32,256]");
     WIW_REQUIRE(!d->geglu || d->bn % 64 == 0, "geglu needs bn % 64 == 0");
     WIW_REQUIRE(d->n_total % 32 == 0, "n_total must be a multiple of 32");
@@ -487,12 +488,12 @@ static int launch_conv_gemm(const wiw_gemm_desc* d, cudaStream_t stream) {
 
     GemmArgs g;
     memset(&g, 0, sizeof(g));
-    g.bx = d->bx; g.by = d->by;
+    g.bx = d->bx; g.by = d->by; g.bz = bz;
     g.dim_x = (int)d->out_dim[1]; g.dim_y = (int)d->out_dim[2];
     g.tiles_x = (g.dim_x + g.bx - 1) / g.bx;
     g.tiles_y = (g.dim_y + g.by - 1) / g.by;
     g.n_tiles = (int)((d->n_total + d->bn - 1) / d->bn);          // a ragged last N-tile loads zero rows (TMA OOB fill) and skips its padded columns
-    const long long m_tiles = (long long)g.tiles_x * g.tiles_y * d->out_dim[3];
+    const long long m_tiles = (long long)g.tiles_x * g.tiles_y * ((d->out_dim[3] + bz - 1) / bz);
     WIW_REQUIRE(m_tiles * g.n_tiles < (1LL << 31), "too many tiles");
     // CTA pairs (cta_group::2, M = 256 per MMA, each CTA stages half of the weight tile) whenever the problem
     // fills the machine; small problems keep single-CTA tiles
@@ -509,8 +510,11 @@ static int launch_conv_gemm(const wiw_gemm_desc* d, cudaStream_t stream) {
     static const int gelu_mode = getenv("WIW_GELU") ? atoi(getenv("WIW_GELU")) : 2;         // 1 = A&S erf (2 MUFU), 2 = tanh-fit erf (1 MUFU)
     static const int epi = getenv("WIW_GEMM_EPI") ? atoi(getenv("WIW_GEMM_EPI")) : 1;       // development aid for A/B runs
     g.warp_store = epi ? 1 : 0;
-    const int sbx = d->bx < 32 ? d->bx : 32, sby = 32 / sbx;                                // one warp's 32 rows as a pixel box
-    for (int q = 0; q < 4; ++q) { g.wx0[q] = (q * 32) % d->bx; g.wy0[q] = (q * 32) / d->bx; }
+    // one warp's 32 rows as a (pixel, row, image) box
+    const int sbx = d->bx < 32 ? d->bx : 32, sby = (d->by < 32 / sbx) ? d->by : 32 / sbx, sbz = 32 / (sbx * sby);
+    for (int q = 0; q < 4; ++q) {
+        g.wx0[q] = (q * 32) % d->bx; g.wy0[q] = ((q * 32) / d->bx) % d->by; g.wz0[q] = (q * 32) / (d->bx * d->by);
+    }
     g.bn = d->bn;
     g.num_taps = d->num_taps; g.chunks_per_tap = d->chunks_per_tap;
     g.geglu = d->geglu ? 1 : 0;
@@ -528,7 +532,7 @@ static int launch_conv_gemm(const wiw_gemm_desc* d, cudaStream_t stream) {
     if (cg == 2) g.tmem_cols = 512;   // pair allocations always take the whole TMEM (as CUTLASS does): both CTAs must see the same base
 
     const int stage_bytes = kBlockM * kBlockK * 2 + (g.bn / cg) * kBlockK * 2;
-    static const int obufs_env = getenv("WIW_GEMM_OBUFS") ? atoi(getenv("WIW_GEMM_OBUFS")) : 4;   // development aid for A/B runs
+    static const int obufs_env = getenv("WIW_GEMM_OBUFS") ? atoi(getenv("WIW_GEMM_OBUFS")) : 2;   // A/B on B200: 4 buffers per group = no gain (the epilogue is not waiting on store reads)
     g.out_bufs = (!g.has_res && !g.has_aux && obufs_env == 4) ? 4 : 2;
     const int fixed = 1024 /*align slack*/ + 2 * g.out_bufs * kEpiChunkBytes + (g.has_res ? kResSlots * kEpiChunkBytes : 0) +
                       (g.has_aux ? kResSlots * kEpiChunkBytes : 0) + 256 /*barriers*/;
@@ -542,7 +546,7 @@ static int launch_conv_gemm(const wiw_gemm_desc* d, cudaStream_t stream) {
     CUtensorMap tm_a, tm_b, tm_out, tm_res, tm_aux;
     {
         uint64_t dims[5], strides[4];
-        uint32_t box[5] = {(uint32_t)kBlockK, (uint32_t)d->bx, 1u, (uint32_t)d->by, 1u};
+        uint32_t box[5] = {(uint32_t)kBlockK, (uint32_t)d->bx, 1u, (uint32_t)d->by, (uint32_t)bz};
         for (int i = 0; i < 5; ++i) dims[i] = (uint64_t)d->a_dim[i];
         for (int i = 1; i < 5; ++i) strides[i - 1] = (uint64_t)d->a_stride[i] * 2;
         if (encode_tmap(&tm_a, d->a, 5, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return 3;
@@ -555,7 +559,7 @@ static int launch_conv_gemm(const wiw_gemm_desc* d, cudaStream_t stream) {
     }
     auto enc_out = [&](CUtensorMap* m, const void* p, const int64_t* st, bool warp_box) -> int {
         uint64_t dims[4], strides[3];
-        uint32_t box[4] = {(uint32_t)kEpiCols, (uint32_t)(warp_box ? sbx : d->bx), (uint32_t)(warp_box ? sby : d->by), 1u};
+        uint32_t box[4] = {(uint32_t)kEpiCols, (uint32_t)(warp_box ? sbx : d->bx), (uint32_t)(warp_box ? sby : d->by), (uint32_t)(warp_box ? sbz : bz)};
         for (int i = 0; i < 4; ++i) dims[i] = (uint64_t)d->out_dim[i];
         for (int i = 1; i < 4; ++i) strides[i - 1] = (uint64_t)st[i] * 2;
         return encode_tmap(m, p, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B);

@@ -36,7 +36,7 @@ class GemmDesc(ctypes.Structure):
         ("num_taps", ctypes.c_int32), ("chunks_per_tap", ctypes.c_int32),
         ("tap_cbase", ctypes.c_int32 * 9), ("tap_ox", ctypes.c_int32 * 9),
         ("tap_p", ctypes.c_int32 * 9), ("tap_oy", ctypes.c_int32 * 9),
-        ("tab_stride", ctypes.c_int32), ("act", ctypes.c_int32),
+        ("tab_stride", ctypes.c_int32), ("act", ctypes.c_int32), ("bz", ctypes.c_int32),
     ]
 
 

@@ -5,6 +5,7 @@ current torch stream and returns immediately.  No op here has a torch fallback.
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 from typing import Optional, Sequence, Tuple
 
@@ -97,6 +98,9 @@ def prep_conv(weight: torch.Tensor, bias: Optional[torch.Tensor], device) -> Gem
 PROFILE = None        # set to a list to record (algorithmic flops, start event, end event) per conv_gemm launch
 
 
+_SMART_BOXES = os.environ.get("WIW_BOX3", "1") != "0"      # development aid for A/B runs: 0 = bx x by x 1 tiles only
+
+
 def _box(width: int) -> Tuple[int, int]:
     """M-tile = by rows of bx pixels (bx*by = 128); bx = largest power of two <= min(width, 128)."""
     bx = 1
@@ -105,11 +109,44 @@ def _box(width: int) -> Tuple[int, int]:
     return bx, 128 // bx
 
 
+def _box3(w: int, h: int, n: int) -> Tuple[int, int, int]:
+    """M-tile of a spatial conv = bx pixels x by rows x bz images (product 128), bx = widest power of two <= min(w, 128):
+    the (by, bz) split that wastes the fewest tile rows -- a 9-row map fills 16 x 8 x 1 tiles to 56 %, 16 x 2 x 4 to 90 %;
+    an 18-row map 32 x 4 x 1 to 90 %, 32 x 2 x 2 to 100 %.  Ties go to fewer images per tile."""
+    bx, _ = _box(w)
+    if not _SMART_BOXES:
+        return bx, 128 // bx, 1
+    best, best_u = (bx, 128 // bx, 1), -1.0
+    by = 128 // bx
+    bz = 1
+    while by >= 1:
+        u = (h / (-(-h // by) * by)) * (n / (-(-n // bz) * bz))
+        if u > best_u + 1e-9:
+            best, best_u = (bx, by, bz), u
+        by //= 2
+        bz *= 2
+    return best
+
+
+def _tbox(s: int, f: int) -> Tuple[int, int]:
+    """M-tile of the temporal conv = bx pixels x by frames (bx*by = 128): the split that wastes the fewest tile rows
+    (S = 144 at the lowest UNet level: 128 x 1 tiles are 56 % full, 16 x 8 tiles 87.5 %); ties go to the wider bx."""
+    best, best_u = (128, 1), -1.0
+    if not _SMART_BOXES:
+        return best
+    for bx in (128, 64, 32, 16, 8):
+        by = 128 // bx
+        u = (s / (-(-s // bx) * bx)) * (f / (-(-f // by) * by))
+        if u > best_u + 1e-9:
+            best, best_u = (bx, by), u
+    return best
+
+
 def _launch(a: torch.Tensor, a_dim, a_stride, gw: GemmWeight, out: torch.Tensor, out_dim, out_stride,
             taps: Sequence[Tuple[int, int, int, int]], bx: int, by: int,
             res: Optional[torch.Tensor], aux: Optional[torch.Tensor], tab: Optional[torch.Tensor],
             tab_div: int, tab_mod: int, s_acc: float, s_res: float, s_aux: float, use_bias: bool = True,
-            act: int = 0) -> None:
+            act: int = 0, bz: int = 1) -> None:
     lib = L.require_device()
     d = L.GemmDesc()
     d.a = a.data_ptr()
@@ -132,6 +169,7 @@ def _launch(a: torch.Tensor, a_dim, a_stride, gw: GemmWeight, out: torch.Tensor,
     d.act = int(act)
     d.s_acc, d.s_res, d.s_aux = float(s_acc), float(s_res), float(s_aux)
     d.bx, d.by, d.bn, d.geglu = bx, by, gw.bn, int(gw.geglu)
+    d.bz = bz
     d.num_taps, d.chunks_per_tap = len(taps), gw.cin // 64
     for i, (cb, ox, p, oy) in enumerate(taps):
         d.tap_cbase[i], d.tap_ox[i], d.tap_p[i], d.tap_oy[i] = cb, ox, p, oy
@@ -176,10 +214,10 @@ def conv3x3(x: torch.Tensor, gw: GemmWeight, res=None, tab=None, tab_div=1, tab_
     assert c == gw.cin and gw.taps == 9
     if out is None:
         out = torch.empty(n, h, w, gw.n, dtype=torch.float16, device=x.device)
-    bx, by = _box(w)
+    bx, by, bz = _box3(w, h, n)
     taps = [(0, kx - 1, 0, ky - 1) for ky in range(3) for kx in range(3)]
     _launch(x, (c, w, 1, h, n), (1, c, w * c, w * c, h * w * c), gw, out, (gw.n, w, h, n), (1, gw.n, w * gw.n, h * w * gw.n),
-            taps, bx, by, res, None, tab, tab_div, tab_mod, s_acc, s_res, 1.0)
+            taps, bx, by, res, None, tab, tab_div, tab_mod, s_acc, s_res, 1.0, bz=bz)
     return out
 
 
@@ -199,7 +237,7 @@ def conv3x3_s2(x: torch.Tensor, gw: GemmWeight, out: Optional[torch.Tensor] = No
     ho, wo = h // 2, w // 2
     if out is None:
         out = torch.empty(n, ho, wo, gw.n, dtype=torch.float16, device=x.device)
-    bx, by = _box(wo)
+    bx, by, bz = _box3(wo, ho, n)
 
     def par(d):           # filter offset d-1 in {-1,0,1} -> (parity, coarse offset)
         return [(1, -1), (0, 0), (1, 0)][d]
@@ -212,7 +250,7 @@ def conv3x3_s2(x: torch.Tensor, gw: GemmWeight, out: Optional[torch.Tensor] = No
             taps.append((px * c, ox, py, oy))
     _launch(x, (2 * c, wo, 2, ho, n), (1, 2 * c, w * c, 2 * w * c, h * w * c), gw, out,
             (gw.n, wo, ho, n), (1, gw.n, wo * gw.n, ho * wo * gw.n), taps, bx, by,
-            None, None, None, 1, 1, 1.0, 1.0, 1.0)
+            None, None, None, 1, 1, 1.0, 1.0, 1.0, bz=bz)
     return out
 
 
@@ -225,8 +263,9 @@ def tconv3(x: torch.Tensor, gw: GemmWeight, res=None, tab=None, tab_div=1, tab_m
     if out is None:
         out = torch.empty(b, f, s, gw.n, dtype=torch.float16, device=x.device)
     taps = [(0, 0, 0, kt - 1) for kt in range(3)]
+    bx, by = _tbox(s, f)
     _launch(x, (c, s, 1, f, b), (1, c, s * c, s * c, f * s * c), gw, out, (gw.n, s, f, b), (1, gw.n, s * gw.n, f * s * gw.n),
-            taps, 128, 1, res, None, tab, tab_div, tab_mod, s_acc, s_res, 1.0)
+            taps, bx, by, res, None, tab, tab_div, tab_mod, s_acc, s_res, 1.0)
     return out
 
 
