@@ -269,7 +269,11 @@ def main():
         roof = {"bound": "tensor", "kernel": "conv_gemm_kernel (tcgen05 implicit GEMM: all Linear/Conv2d/Conv3d of the UNet)",
                 "achieved": round(ach, 1), "peak": peak, "unit": "TFLOP/s", "frac": round(ach / peak, 4), "peak_source": how,
                 "launches_per_unet_forward": len(prof), "algorithmic_tflop_per_unet_forward": round(g_flop / 1e12, 3),
-                "kernel_ms_per_unet_forward": round(g_ms, 3), "share_of_unet_forward": round(g_ms / unet_ms, 3), "traffic": None}
+                "kernel_ms_per_unet_forward": round(g_ms, 3), "share_of_unet_forward": round(g_ms / unet_ms, 3),
+                # dram__bytes_read.sum + dram__bytes_write.sum of ONE representative launch from the committed `ncu --set full`
+                # capture (profiles/r01_ncu_full_v5.md): conv3x3 28x72x128 320->320, algorithmic bytes 332.1e6 (traffic / algorithmic = 0.91)
+                "traffic": 300.9e6, "traffic_launch": "conv3x3 28x72x128 320->320 (K=2880, N=320): 167.1 MB read + 133.8 MB written, "
+                                                      "algorithmic 332.1 MB; per-shape table in profiles/r01_ncu_full_v5.md"}
         stages = {"unet_forward_ms": round(unet_ms, 2), "vae_decode_ms": round(dec_ms, 2),
                   "unet_forward_tflops": round((TFLOP_UNET_FWD - TFLOP_UNET_REMOVABLE) / unet_ms * 1e3, 1),
                   "unet_forward_frac_of_peak": round((TFLOP_UNET_FWD - TFLOP_UNET_REMOVABLE) / unet_ms * 1e3 / peak, 4),

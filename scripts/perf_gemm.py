@@ -37,16 +37,20 @@ for (m, c) in [(258048, 320), (64512, 640), (16128, 1280)]:
     for (name, n, geglu) in [("qkv", 3 * c, False), ("proj", c, False), ("ff1_geglu", 8 * c, True)]:
         if ONLY and ONLY not in name:
             continue
+        if ONLY == "res":
+            continue
         gw = ops.prep_linear(torch.randn(n, c) * c ** -0.5, torch.randn(n), DEV, geglu=geglu)
         out = torch.empty(m, gw.n // 2 if geglu else gw.n, device=DEV, dtype=torch.half)
         rec(f"linear {name} M={m} K={c} N={n} bn={gw.bn}", timeit(lambda: ops.linear(x, gw, out=out)), 2.0 * m * c * n)
-    if ONLY:
+    if ONLY and ONLY != "res":
         continue
     x4 = torch.randn(m, 4 * c, device=DEV).half()
     res = torch.randn(m, c, device=DEV).half()
     gw = ops.prep_linear(torch.randn(c, 4 * c) * (4 * c) ** -0.5, torch.randn(c), DEV)
     out = torch.empty(m, c, device=DEV, dtype=torch.half)
     rec(f"linear ff2+res M={m} K={4*c} N={c} bn={gw.bn}", timeit(lambda: ops.linear(x4, gw, res=res, out=out)), 2.0 * m * 4 * c * c)
+    gwp = ops.prep_linear(torch.randn(c, c) * c ** -0.5, torch.randn(c), DEV)
+    rec(f"linear proj+res M={m} K={c} N={c} bn={gwp.bn}", timeit(lambda: ops.linear(x, gwp, res=res, out=out)), 2.0 * m * c * c)
     del x4, res
 
 if ONLY:

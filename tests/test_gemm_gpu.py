@@ -79,7 +79,9 @@ def test_geglu(c):
     close(y, val * F.gelu(gate), f"geglu C={c}")
 
 
-@pytest.mark.parametrize("n,h,w,cin,cout", [(3, 9, 16, 64, 128), (2, 16, 128, 128, 320), (2, 5, 8, 64, 64), (1, 2, 4, 128, 64), (2, 72, 128, 64, 32), (2, 18, 32, 128, 640)])
+@pytest.mark.parametrize("n,h,w,cin,cout", [(3, 9, 16, 64, 128), (2, 16, 128, 128, 320), (2, 5, 8, 64, 64), (1, 2, 4, 128, 64), (2, 72, 128, 64, 32), (2, 18, 32, 128, 640),
+                                             # M-tiles spanning several images (bz > 1): exact and ragged image counts
+                                             (28, 9, 16, 64, 64), (5, 9, 16, 64, 96), (7, 18, 32, 64, 64), (3, 1, 2, 64, 64)])
 def test_conv3x3(n, h, w, cin, cout):
     x = rnd(n, h, w, cin, seed=1).half().to(DEV)
     wt, b = rnd(cout, cin, 3, 3, seed=2, scale=(9 * cin) ** -0.5), rnd(cout, seed=3)
@@ -115,7 +117,8 @@ def test_conv3x3_stride2(n, h, w, c, cout):
     close(y, ref, "conv s2")
 
 
-@pytest.mark.parametrize("b_,f,s,c", [(2, 5, 144, 64), (1, 14, 128, 128), (2, 8, 2, 64)])
+@pytest.mark.parametrize("b_,f,s,c", [(2, 5, 144, 64), (1, 14, 128, 128), (2, 8, 2, 64), (2, 14, 144, 64), (1, 14, 576, 64),
+                                        (2, 3, 40, 64)])
 def test_tconv3(b_, f, s, c):
     x = rnd(b_, f, s, c, seed=1).half().to(DEV)
     wt, b = rnd(c, c, 3, 1, 1, seed=2, scale=(3 * c) ** -0.5), rnd(c, seed=3)

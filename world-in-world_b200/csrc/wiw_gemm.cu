@@ -26,7 +26,7 @@ constexpr int kBlockK = 64;                    // 64 fp16 = one 128-byte swizzle
 constexpr int kEpiCols = 32;                   // epilogue chunk: 32 fp16 = 64-byte rows (SWIZZLE_64B)
 constexpr int kEpiChunkBytes = kBlockM * kEpiCols * 2;   // 8 KB
 constexpr int kMaxOutBufs = 8;                 // staging chunks: 2 or 4 per epilogue group (GemmArgs::out_bufs)
-constexpr int kResSlots = 4;
+constexpr int kMaxResSlots = 8;                // residual / aux chunk slots: GemmArgs::res_slots (4 or 8)
 constexpr int kMaxStages = 8;
 constexpr int kThreads = 11 * 32;              // TMA, MMA, epilogue loader, 2 x 4 epilogue warps
 constexpr int kSmemBudget = 227 * 1024;
@@ -39,6 +39,7 @@ struct GemmArgs {
     int tab_div, tab_mod, n_total, tmem_cols;
     int tab_stride, act, out_total;
     int dbg;                                      // development aid: bit 0 = skip TMA loads, bit 1 = skip MMA issue (timing only)
+    int res_slots;                                // residual (aux) chunks in flight: 8 lets a whole tile's residual prefetch behind the MMAs
     int out_bufs;                                 // staging buffers per epilogue group: 4 when no residual / aux slots compete for smem, else 2
     int warp_store;                               // 1: every epilogue warp stores its own 32-row slab (no CTA barriers); 0: one store per 128-row chunk
     int wx0[4], wy0[4], wz0[4];                   // (pixel, row, image) offset of epilogue warp q's 32 rows inside the M-tile
@@ -85,16 +86,16 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     const uint32_t stage_bytes = a_bytes + b_bytes;
     const uint32_t out_base = smem_base + g.stages * stage_bytes;
     const uint32_t res_base = out_base + 2 * g.out_bufs * kEpiChunkBytes;
-    const uint32_t aux_base = res_base + (g.has_res ? kResSlots * kEpiChunkBytes : 0);
-    const uint32_t bar_base = aux_base + (g.has_aux ? kResSlots * kEpiChunkBytes : 0);
+    const uint32_t aux_base = res_base + (g.has_res ? g.res_slots * kEpiChunkBytes : 0);
+    const uint32_t bar_base = aux_base + (g.has_aux ? g.res_slots * kEpiChunkBytes : 0);
     // barrier slots (8 B each)
     const uint32_t bar_full = bar_base;                         // [kMaxStages]
     const uint32_t bar_empty = bar_full + 8 * kMaxStages;       // [kMaxStages]
     const uint32_t bar_tfull = bar_empty + 8 * kMaxStages;      // [2]
     const uint32_t bar_tempty = bar_tfull + 16;                 // [2]
-    const uint32_t bar_rfull = bar_tempty + 16;                 // [kResSlots]
-    const uint32_t bar_rempty = bar_rfull + 8 * kResSlots;      // [kResSlots]
-    const uint32_t tmem_slot = bar_rempty + 8 * kResSlots;      // uint32
+    const uint32_t bar_rfull = bar_tempty + 16;                 // [kMaxResSlots]
+    const uint32_t bar_rempty = bar_rfull + 8 * kMaxResSlots;   // [kMaxResSlots]
+    const uint32_t tmem_slot = bar_rempty + 8 * kMaxResSlots;   // uint32
     uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
     const int warp = threadIdx.x >> 5;
@@ -120,7 +121,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             mbar_init(bar_tfull + 8 * i, 1);
             mbar_init(bar_tempty + 8 * i, 8 * CG);       // one arrival per epilogue warp of every CTA in the pair
         }
-        for (int i = 0; i < kResSlots; ++i) {
+        for (int i = 0; i < kMaxResSlots; ++i) {
             mbar_init(bar_rfull + 8 * i, 1);
             mbar_init(bar_rempty + 8 * i, 128);
         }
@@ -245,7 +246,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                         if (g.has_aux) tma_load_4d(aux_base + rs * kEpiChunkBytes, &tm_aux, bar_rfull + 8 * rs, c0 + j * kEpiCols, t.x0, t.y0, t.img);
                     }
                     __syncwarp();
-                    if (++rs == kResSlots) { rs = 0; rph ^= 1; }
+                    if (++rs == g.res_slots) { rs = 0; rph ^= 1; }
                 }
             }
         }
@@ -375,8 +376,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 }
                 if (has_epi_loads) {
                     const long long n = chunk_base + j;                       // global chunk index of this CTA
-                    const int rs = int(n % kResSlots);
-                    const uint32_t rph = uint32_t(n / kResSlots) & 1u;
+                    const int rs = int(n % g.res_slots);
+                    const uint32_t rph = uint32_t(n / g.res_slots) & 1u;
                     mbar_wait(bar_rfull + 8 * rs, rph);
                     const uint8_t* gen = smem_raw + (res_base - smem_u32(smem_raw));
                     if (g.has_res) {
@@ -501,7 +502,7 @@ static int launch_conv_gemm(const wiw_gemm_desc* d, cudaStream_t stream) {
     // Measured on B200 (profiles/r01_mma_cost.md, r01_gemm_pair_ab.md): a single-CTA tile is bound by shared-memory
     // bandwidth (TMA writes + UMMA reads of the same stage, 128 B/clk), so halving the weight bytes per CTA wins on
     // every shape except the tiny K=320, N=320 projection, where the pair handshakes cost ~3 %.
-    const bool pair_shape = !(d->k_total <= 320 && d->n_total <= 320);
+    const bool pair_shape = !(d->k_total <= 320 && d->n_total <= 320) || (d->res != nullptr && d->aux == nullptr);   // (pairs leave room for 8 residual slots)
     int cg = (pair_shape && m_tiles * g.n_tiles >= 2LL * num_sms()) ? 2 : 1;
     if (force_cg == 1 || force_cg == 2) cg = force_cg;
     g.total_tiles = (int)(((m_tiles + cg - 1) / cg) * g.n_tiles);
@@ -534,8 +535,18 @@ static int launch_conv_gemm(const wiw_gemm_desc* d, cudaStream_t stream) {
     const int stage_bytes = kBlockM * kBlockK * 2 + (g.bn / cg) * kBlockK * 2;
     static const int obufs_env = getenv("WIW_GEMM_OBUFS") ? atoi(getenv("WIW_GEMM_OBUFS")) : 2;   // A/B on B200: 4 buffers per group = no gain (the epilogue is not waiting on store reads)
     g.out_bufs = (!g.has_res && !g.has_aux && obufs_env == 4) ? 4 : 2;
-    const int fixed = 1024 /*align slack*/ + 2 * g.out_bufs * kEpiChunkBytes + (g.has_res ? kResSlots * kEpiChunkBytes : 0) +
-                      (g.has_aux ? kResSlots * kEpiChunkBytes : 0) + 256 /*barriers*/;
+    // 4 residual slots cover less than one tile (5-8 chunks): the load of a tile's last chunks is only issued once the epilogue
+    // has freed a slot and its HBM latency lands on the epilogue.  8 slots hold a whole tile; taken when only one of res / aux
+    // competes for shared memory and at least 4 pipeline stages remain.
+    static const int rslots_env = getenv("WIW_GEMM_RSLOTS") ? atoi(getenv("WIW_GEMM_RSLOTS")) : 8;   // development aid for A/B runs
+    g.res_slots = 4;
+    {
+        const int sb = kBlockM * kBlockK * 2 + (g.bn / cg) * kBlockK * 2;
+        const int fixed8 = 1024 + 2 * g.out_bufs * kEpiChunkBytes + 8 * kEpiChunkBytes + 512;
+        if (rslots_env == 8 && (g.has_res != g.has_aux) && (kSmemBudget - fixed8) / sb >= 4) g.res_slots = 8;
+    }
+    const int fixed = 1024 /*align slack*/ + 2 * g.out_bufs * kEpiChunkBytes + (g.has_res ? g.res_slots * kEpiChunkBytes : 0) +
+                      (g.has_aux ? g.res_slots * kEpiChunkBytes : 0) + 512 /*barriers*/;
     int stages = (kSmemBudget - fixed) / stage_bytes;
     if (stages > kMaxStages) stages = kMaxStages;
     WIW_REQUIRE(stages >= 2, "not enough shared memory for 2 pipeline stages");
