@@ -502,7 +502,7 @@ static int launch_conv_gemm(const wiw_gemm_desc* d, cudaStream_t stream) {
     // Measured on B200 (profiles/r01_mma_cost.md, r01_gemm_pair_ab.md): a single-CTA tile is bound by shared-memory
     // bandwidth (TMA writes + UMMA reads of the same stage, 128 B/clk), so halving the weight bytes per CTA wins on
     // every shape except the tiny K=320, N=320 projection, where the pair handshakes cost ~3 %.
-    const bool pair_shape = !(d->k_total <= 320 && d->n_total <= 320) || (d->res != nullptr && d->aux == nullptr);   // (pairs leave room for 8 residual slots)
+    const bool pair_shape = !(d->k_total <= 320 && d->n_total <= 320);
     int cg = (pair_shape && m_tiles * g.n_tiles >= 2LL * num_sms()) ? 2 : 1;
     if (force_cg == 1 || force_cg == 2) cg = force_cg;
     g.total_tiles = (int)(((m_tiles + cg - 1) / cg) * g.n_tiles);
@@ -535,10 +535,9 @@ static int launch_conv_gemm(const wiw_gemm_desc* d, cudaStream_t stream) {
     const int stage_bytes = kBlockM * kBlockK * 2 + (g.bn / cg) * kBlockK * 2;
     static const int obufs_env = getenv("WIW_GEMM_OBUFS") ? atoi(getenv("WIW_GEMM_OBUFS")) : 2;   // A/B on B200: 4 buffers per group = no gain (the epilogue is not waiting on store reads)
     g.out_bufs = (!g.has_res && !g.has_aux && obufs_env == 4) ? 4 : 2;
-    // 4 residual slots cover less than one tile (5-8 chunks): the load of a tile's last chunks is only issued once the epilogue
-    // has freed a slot and its HBM latency lands on the epilogue.  8 slots hold a whole tile; taken when only one of res / aux
-    // competes for shared memory and at least 4 pipeline stages remain.
-    static const int rslots_env = getenv("WIW_GEMM_RSLOTS") ? atoi(getenv("WIW_GEMM_RSLOTS")) : 8;   // development aid for A/B runs
+    // 8 residual slots (a whole tile's residual in flight) were tried and measured 5-17 % slower than 4: the shared memory is
+    // worth more as A/B pipeline stages (profiles/r01_perf_gemm_v9_res_slots.txt).
+    static const int rslots_env = getenv("WIW_GEMM_RSLOTS") ? atoi(getenv("WIW_GEMM_RSLOTS")) : 4;   // A/B on B200: 8 slots = 5-17 % SLOWER (they cost pipeline stages)
     g.res_slots = 4;
     {
         const int sb = kBlockM * kBlockK * 2 + (g.bn / cg) * kBlockK * 2;

@@ -257,14 +257,17 @@ template <int LPR, int VPL>
 __global__ void __launch_bounds__(256, 2)
 layernorm_lpr_kernel(const __half* __restrict__ x, __half* __restrict__ y, const float* __restrict__ gamma,
                      const float* __restrict__ beta, const __half* __restrict__ tab, int tab_div, int tab_mod,
-                     long long M, int C, float eps, int groups_per_warp) {
+                     long long M, int C, float eps, long long groups, long long total_warps) {
     constexpr int RPW = 32 / LPR;                       // rows per warp per group
     const int lane = threadIdx.x & 31;
     const int sub = lane / LPR, j = lane % LPR;
     const int nvec = C >> 3;
     const long long warp_global = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const long long g0 = warp_global * groups_per_warp;
-    if (g0 * RPW >= M) return;
+    if (warp_global >= total_warps) return;
+    // contiguous, balanced share of the row groups: [w * G / W, (w + 1) * G / W)
+    const long long g0 = warp_global * groups / total_warps;
+    const int groups_per_warp = (int)((warp_global + 1) * groups / total_warps - g0);
+    if (groups_per_warp <= 0) return;
     uint32_t gpk[VPL][4], bpk[VPL][4];                  // gamma / beta of this lane's channels as half2
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
@@ -726,9 +729,16 @@ extern "C" int wiw_groupnorm(const void* x, void* y, int samples, long long rows
         WIW_CHECK_CUDA(cudaGetLastError());
         return 0;
     }
-    // ~8 CTAs per SM, each thread keeps kUnroll rows in flight
+    // Whole waves of resident CTAs: 43 chunks x 28 frames = 1204 CTAs on 592 resident slots is 2.03 waves -- the 0.03 costs a
+    // full CTA time.  Round the chunk count DOWN so samples * chunks <= waves * occupancy * SMs.
+    static const int wavefit = getenv("WIW_WAVEFIT") ? atoi(getenv("WIW_WAVEFIT")) : 1;       // development aid for A/B runs
+    int occ_s = 4, occ_a = 4;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s, gn_stats_kernel, threads, (size_t)(2 * RL + 2) * C * sizeof(float));
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_a, gn_apply_kernel, threads, 0);
+    if (occ_s < 1) occ_s = 1;
+    if (occ_a < 1) occ_a = 1;
     auto pick_chunks = [&](int target_ctas) {
-        long long chunks = (target_ctas + samples - 1) / samples;
+        long long chunks = wavefit ? target_ctas / samples : (target_ctas + samples - 1) / samples;
         if (chunks > kGnMaxChunks) chunks = kGnMaxChunks;
         if (chunks < 1) chunks = 1;
         long long rpc = (rows_per_sample + chunks - 1) / chunks;
@@ -736,7 +746,7 @@ extern "C" int wiw_groupnorm(const void* x, void* y, int samples, long long rows
         if (rpc < min_rows) rpc = min_rows;
         return rpc;
     };
-    const long long rpc = pick_chunks(8 * num_sms());
+    const long long rpc = pick_chunks(wavefit ? 2 * occ_s * num_sms() : 8 * num_sms());
     const int chunks = (int)((rows_per_sample + rpc - 1) / rpc);
     gn_stats_kernel<<<dim3(chunks, samples), threads, (size_t)(2 * RL + 2) * C * sizeof(float), stream>>>(
         static_cast<const __half*>(x), partial, rows_per_sample, C, G, (int)rpc, vpr, RL);
@@ -744,7 +754,7 @@ extern "C" int wiw_groupnorm(const void* x, void* y, int samples, long long rows
     const int warps = samples * G;
     gn_finalize_kernel<<<(warps * 32 + 255) / 256, 256, 0, stream>>>(partial, stats, samples, G, chunks, count, eps);
     WIW_CHECK_CUDA(cudaGetLastError());
-    const long long arpc = pick_chunks(16 * num_sms());
+    const long long arpc = pick_chunks(wavefit ? 4 * occ_a * num_sms() : 16 * num_sms());
     const int achunks = (int)((rows_per_sample + arpc - 1) / arpc);
     gn_apply_kernel<<<dim3(achunks, samples), threads, 0, stream>>>(
         static_cast<const __half*>(x), static_cast<__half*>(y), stats, gamma, beta, rows_per_sample, C, G, (int)arpc, vpr, RL,
@@ -765,17 +775,23 @@ extern "C" int wiw_layernorm(const void* x, void* y, long long M, int C, const f
     __half* yo = static_cast<__half*>(y);
     const int nvec = C / 8;
     static const int norm_v = getenv("WIW_NORM_V") ? atoi(getenv("WIW_NORM_V")) : 3;          // 3 = lane-group kernel (default), 1 = one warp per row, 2 = TMA-ring streaming
+    static const int wavefit = getenv("WIW_WAVEFIT") ? atoi(getenv("WIW_WAVEFIT")) : 1;       // development aid for A/B runs
     if (norm_v == 3) {
         auto launch = [&](auto kern, int lpr) -> int {
             const int rpw = 32 / lpr;
             const long long groups = (M + rpw - 1) / rpw;
-            // enough warps for ~4 waves of 16 warps per SM, at most 8 row groups per warp
-            long long gpw = groups / ((long long)num_sms() * 16 * 4);
-            if (gpw < 1) gpw = 1;
-            if (gpw > 8) gpw = 8;
-            const long long warps = (groups + gpw - 1) / gpw;
-            const unsigned grid = (unsigned)((warps + 7) / 8);
-            kern<<<grid, 256, 0, stream>>>(xi, yo, gamma, beta, tab, tab_div, tab_mod, M, C, eps, (int)gpw);
+            // whole waves of resident CTAs (no ragged last wave): W = waves * occupancy * SMs CTAs of 8 warps, the row groups
+            // split evenly over the warps (~8-16 groups each so gamma / beta and the prefetch pipeline amortise)
+            int occ = 2;
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, 0);
+            if (occ < 1) occ = 1;
+            const long long slots = (long long)occ * num_sms();
+            long long waves = (groups + slots * 8 * 12 - 1) / (slots * 8 * 12);
+            if (waves < 1) waves = 1;
+            long long blocks = wavefit ? waves * slots : (groups + 8 * 6 - 1) / (8 * 6);
+            if (blocks * 8 > groups) blocks = (groups + 7) / 8;
+            const long long warps = blocks * 8 < groups ? blocks * 8 : groups;
+            kern<<<(unsigned)blocks, 256, 0, stream>>>(xi, yo, gamma, beta, tab, tab_div, tab_mod, M, C, eps, groups, warps);
             WIW_CHECK_CUDA(cudaGetLastError());
             return 0;
         };
