@@ -18,8 +18,9 @@ from wiw_b200 import wm_worker as W  # noqa: E402
 class FakeNavigator:
     def __init__(self, args):
         self.args = args
+        self.device = torch.device("cpu")
 
-    def inference(self, actions, images_u8, out_width=None, out_height=None, latents=None, on_device=False):
+    def inference(self, actions, images_u8, out_width=None, out_height=None, latents=None, on_device=False, seeds=None):
         b, F = actions.shape[0], self.args.num_frames
         assert images_u8.shape[1] in (3, 4) and images_u8.dtype == np.uint8
         acts = torch.diagonal(actions, dim1=-2, dim2=-1)

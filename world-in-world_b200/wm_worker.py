@@ -174,6 +174,17 @@ def save_predict(video: np.ndarray, b_action, save_dirs: List[str]) -> None:
             json.dump(acts.tolist() if hasattr(acts, "tolist") else acts, f, indent=2, ensure_ascii=False)
 
 
+def save_predict_u8(video_u8: np.ndarray, b_action, save_dirs: List[str]) -> None:
+    """save_predict for frames that already went through the reference's resize + double quantisation (uint8 [b,T,3,H,W])."""
+    from PIL import Image
+    for clip, acts, folder in zip(video_u8, b_action, save_dirs):
+        os.makedirs(folder, exist_ok=True)
+        for i, fr in enumerate(clip):
+            Image.fromarray(np.ascontiguousarray(fr.transpose(1, 2, 0))).save(os.path.join(folder, f"{i}.jpg"))
+        with open(os.path.join(folder, "action_seq.json"), "w") as f:
+            json.dump(acts.tolist() if hasattr(acts, "tolist") else acts, f, indent=2, ensure_ascii=False)
+
+
 # ----------------------------------------------------------------------------- the model holder
 class Navigator:
     """Counterpart of FTsvd/eval_inference.py:85-266: owns the pipeline and a persistent, seeded generator."""
@@ -191,7 +202,7 @@ class Navigator:
 
     @torch.no_grad()
     def inference(self, actions: torch.Tensor, images_u8: np.ndarray, out_width=None, out_height=None,
-                  latents: Optional[torch.Tensor] = None, on_device: bool = False):
+                  latents: Optional[torch.Tensor] = None, on_device: bool = False, seeds: Optional[List[int]] = None):
         """actions int64/float [b, F, F] (action_ids_idx_encode); images_u8 uint8 [b, 3, H, W].
         Returns uint8 frames [b, F, 3, H, W] (the pipeline's PIL frames).  Branches run one after another
         (request batch 1 per UNet call, as the reference deployment does)."""
@@ -208,9 +219,19 @@ class Navigator:
             img = torch.nn.functional.interpolate(img, size=(H, W), mode="bilinear", antialias=True)
         emb = frontend.encode_image_clip(img, self.image_encoder)                             # [b, 1, D]
         pre = img * 2.0 - 1.0                                                                # video_processor.preprocess
-        noise = torch.randn(pre.shape, generator=self.generator, device=dev, dtype=pre.dtype)   # pipeline :521-523
+        if seeds is not None:
+            # sharded serving: one generator state per branch, so a branch's noise does not depend on which rank rolls it out
+            gens = [torch.Generator(device=dev).manual_seed(int(sd)) for sd in seeds]
+            noise = torch.stack([torch.randn(pre.shape[1:], generator=g, device=dev, dtype=pre.dtype) for g in gens])
+        else:
+            noise = torch.randn(pre.shape, generator=self.generator, device=dev, dtype=pre.dtype)   # pipeline :521-523
         image_latents = frontend.vae_encode_mode(self.vae_encoder_sd, pre + self.noise_aug_strength * noise).to(torch.float16)
-        if latents is None:                                                                  # prepare_latents :325-362
+        if latents is None and seeds is not None:
+            raw = torch.stack([torch.randn((F, 4, H // 8, W // 8), generator=g, device=dev, dtype=torch.float16) for g in gens])
+            diag = torch.diagonal(actions, dim1=-2, dim2=-1)
+            for i in range(b):
+                sample_latent_noise_(raw[i], diag[i])
+        elif latents is None:                                                                # prepare_latents :325-362
             raw = torch.randn((b, F, 4, H // 8, W // 8), generator=self.generator, device=dev, dtype=torch.float16)
             diag = torch.diagonal(actions, dim1=-2, dim2=-1)                                 # decode_action_seq_frames :826-844
             for i in range(b):
@@ -231,6 +252,15 @@ class WorldModelWorker:
     def __init__(self, args, navigator: Navigator):
         self.args, self.nav = args, navigator
 
+    def resized_frames(self, frames: torch.Tensor) -> torch.Tensor:
+        """uint8 [b, F, 3, H, W] on the device -> uint8 [b, F, 3, H_out, W_out]: PIL BICUBIC resize + the reference's double
+        quantisation, byte-exact, on the GPU (wiw_resize_bicubic_u8)."""
+        key = (frames.shape[-2], frames.shape[-1], self.args.out_height, self.args.out_width)
+        if getattr(self, "_resizer_key", None) != key:
+            from .resize import GpuResizer
+            self._resizer, self._resizer_key = GpuResizer(*key, device=frames.device), key
+        return self._resizer(frames)
+
     def do_some_tasks(self, input_dict: dict) -> dict:
         save_dirs = list(input_dict.get("save_dirs", []))
         try:
@@ -249,13 +279,8 @@ class WorldModelWorker:
             action_ids = action_ids_idx_encode(b_action)
             frames = self.nav.inference(action_ids, b_image, self.args.out_width, self.args.out_height, on_device=True)
             if return_objects:
-                # PIL BICUBIC resize + the reference's double quantisation, byte-exact, on the GPU (wiw_resize_bicubic_u8):
                 # only the 480x480 uint8 result crosses PCIe
-                key = (frames.shape[-2], frames.shape[-1], self.args.out_height, self.args.out_width)
-                if getattr(self, "_resizer_key", None) != key:
-                    from .resize import GpuResizer
-                    self._resizer, self._resizer_key = GpuResizer(*key, device=frames.device), key
-                return {"pred_frames": self._resizer(frames).cpu().numpy(), "save_dirs": save_dirs}
+                return {"pred_frames": self.resized_frames(frames).cpu().numpy(), "save_dirs": save_dirs}
             video = images_to_tensor(frames.cpu().numpy(), save_size=(self.args.out_width, self.args.out_height)).numpy()
             save_predict(video, b_action, save_dirs)
             return {"save_dirs": save_dirs}
@@ -264,6 +289,75 @@ class WorldModelWorker:
             n = len(save_dirs)
             zeros = np.zeros((n, self.args.num_frames, 3, self.args.out_height, self.args.out_width), dtype=np.uint8)
             return {"pred_frames": zeros, "save_dirs": save_dirs}
+
+
+class ShardedWorldModelWorker(WorldModelWorker):
+    """One worker that owns R GPUs of a node (BASELINE configs[2]): rank 0 is the process the manager
+    spawned (stdin / write-fd); ranks 1..R-1 are helper processes it started.  Per request rank 0 broadcasts the payload
+    (control plane, gloo), rank r rolls out branches r, r+R, ... with no per-step communication, and ONE all-gather of the
+    resized uint8 frames (NCCL over NVLink on the GPU box) returns the result to rank 0, which answers the manager.
+    Launch with `--gpus R` and run the manager with a batch size >= the request size so it does not pre-split the batch."""
+
+    def __init__(self, args, navigator, rank: int, world: int):
+        super().__init__(args, navigator)
+        self.rank, self.world, self.serial = rank, world, 0
+
+    def _local(self, input_dict: dict):
+        from .sharding import branch_indices
+        b = len(input_dict["save_dirs"])
+        idx = branch_indices(b, self.rank, self.world)
+        local = {k: ([v[i] for i in idx] if isinstance(v, list) else (v[idx] if isinstance(v, np.ndarray) else v))
+                 for k, v in input_dict.items()}
+        return b, idx, local
+
+    def serve_request(self, input_dict: Optional[dict]) -> Optional[dict]:
+        """Collective: every rank calls it once per request (rank 0 with the payload, the helpers with None)."""
+        import torch.distributed as dist
+        from .sharding import gather_frames
+        box = [input_dict]
+        dist.broadcast_object_list(box, src=0)
+        req = box[0]
+        if req is None:                                   # shutdown
+            return None
+        self.serial += 1
+        try:
+            check_inputdict(req)
+            assert name_matches(req["request_model_name"], WORLD_MODEL_NAME), f"request_model_name: {req['request_model_name']}"
+            b, idx, loc = self._local(req)
+            dev = self.nav.device
+            F, Ho, Wo = self.args.num_frames, self.args.out_height, self.args.out_width
+            if idx:
+                b_image = loc.get("b_image")
+                if b_image is None:
+                    from PIL import Image
+                    b_image = np.stack([np.asarray(Image.open(os.path.join(d, "cond_rgb.png")).convert("RGB")).transpose(2, 0, 1)
+                                        for d in loc["save_dirs"]])
+                acts = np.asarray(loc["b_action"])
+                seeds = [1 + 1000003 * self.serial + i for i in idx]          # per (request, branch): independent of the rank count
+                frames = self.nav.inference(action_ids_idx_encode(acts), b_image, Wo, Ho, on_device=True, seeds=seeds)
+                small = self.resized_frames(frames)
+            else:
+                acts = np.zeros((0, F), np.int64)
+                small = torch.zeros((0, F, 3, Ho, Wo), dtype=torch.uint8, device=dev)
+            if bool(req.get("return_objects")):
+                out = gather_frames(small, b)                                  # the one data-path collective
+                return {"pred_frames": out.cpu().numpy(), "save_dirs": list(req["save_dirs"])} if self.rank == 0 else {}
+            if idx:                                                            # files mode: every rank writes its own branches
+                save_predict_u8(small.cpu().numpy(), acts, loc["save_dirs"])
+            dist.barrier()
+            return {"save_dirs": list(req["save_dirs"])} if self.rank == 0 else {}
+        except Exception:
+            traceback.print_exc()
+            n = len(req.get("save_dirs", [])) if isinstance(req, dict) else 0
+            zeros = np.zeros((n, self.args.num_frames, 3, self.args.out_height, self.args.out_width), dtype=np.uint8)
+            return {"pred_frames": zeros, "save_dirs": list(req.get("save_dirs", []))}
+
+    def do_some_tasks(self, input_dict: dict) -> dict:            # rank 0's task_fn
+        return self.serve_request(input_dict)
+
+    def helper_loop(self) -> None:                                # ranks 1..R-1
+        while self.serve_request(None) is not None:
+            pass
 
 
 # ----------------------------------------------------------------------------- construction
@@ -288,6 +382,11 @@ def build_parser() -> argparse.ArgumentParser:
     p.add_argument("--random_init", action="store_true")
     p.add_argument("--num_inference_steps", type=int, default=30)
     p.add_argument("--tiny", action="store_true")
+    # sharded serving (BASELINE configs[2]): this worker owns `--gpus` GPUs of the node; --rank / --master_port are set by
+    # rank 0 when it starts its helper processes
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--rank", type=int, default=0)
+    p.add_argument("--master_port", type=int, default=0)
     return p
 
 
@@ -332,16 +431,47 @@ def build_worker(args) -> WorldModelWorker:
                                                              torch_dtype=torch.float16).to(dev).eval()
     rollout = Rollout(UNetEngine(ucfg, usd, dev), VAEDecoderEngine(vcfg, vsd, dev), dev)
     del usd, vsd
-    return WorldModelWorker(args, Navigator(args, rollout, clip, esd, dev))
+    nav = Navigator(args, rollout, clip, esd, dev)
+    if getattr(args, "gpus", 1) > 1:
+        return ShardedWorldModelWorker(args, nav, args.rank, args.gpus)
+    return WorldModelWorker(args, nav)
+
+
+def _free_port() -> int:
+    import socket
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
 
 
 def main(argv: List[str]) -> None:
     pipe_fd = int(argv[-1])                                    # eval_inference.py:271
     args, _unknown = build_parser().parse_known_args(argv[:-1])
     print(f"[igenex worker] All Args:\n {args}")
+    helpers = []
+    if args.gpus > 1:
+        import subprocess
+        import torch.distributed as dist
+        if args.rank == 0:                                     # the process the manager spawned: start ranks 1..R-1
+            args.master_port = args.master_port or _free_port()
+            base = [a for a in argv[:-1] if not a.startswith(("--rank", "--master_port", "--device"))]
+            for r in range(1, args.gpus):
+                helpers.append(subprocess.Popen([sys.executable, os.path.abspath(__file__)] + base +
+                                                [f"--rank={r}", f"--master_port={args.master_port}", "-1"], stdin=subprocess.DEVNULL))
+        args.device = f"cuda:{args.rank}"
+        torch.cuda.set_device(args.rank)
+        dist.init_process_group("cpu:gloo,cuda:nccl", init_method=f"tcp://127.0.0.1:{args.master_port}", rank=args.rank,
+                                world_size=args.gpus, device_id=torch.device(args.device))
     worker = build_worker(args)
     print(f"[igenex worker] Initialized navigator with device {args.device}.")
+    if args.gpus > 1 and args.rank > 0:
+        worker.helper_loop()
+        return
     worker_main(pipe_fd, worker.do_some_tasks)
+    if args.gpus > 1:
+        worker.serve_request(None)                             # tell the helpers to exit
+        for h in helpers:
+            h.wait(timeout=120)
 
 
 if __name__ == "__main__":
