@@ -26,6 +26,8 @@ class FakeNavigator:
         acts = torch.diagonal(actions, dim1=-2, dim2=-1)
         out = torch.empty((b, F, 3, self.args.height, self.args.width), dtype=torch.uint8)
         for i in range(b):
+            if int(acts[i].sum()) == 77:
+                raise RuntimeError("stub: injected failure for this branch")
             for t in range(F):
                 out[i, t] = int((int(acts[i].sum()) * 7 + t) % 256)
         return out

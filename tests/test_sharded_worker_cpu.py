@@ -57,6 +57,12 @@ def _run(rank, world, port, tmp, q):
                                              for d in req["save_dirs"])
     bad = worker.do_some_tasks({**req, "request_model_name": "cosmos", "return_objects": [True] * 3})
     ok &= bad["pred_frames"].shape == (3, 8, 3, 20, 24) and int(bad["pred_frames"].max()) == 0      # all ranks reject alike: no hang
+    acts_bad = acts.copy()
+    acts_bad[1] = [4, 73, 0, 0, 0, 0, 0, 0]                       # branch 1 lives on rank 1 and raises there only
+    out = worker.do_some_tasks({**req, "b_action": acts_bad, "return_objects": [True] * 3})
+    ok &= out["pred_frames"].shape == (3, 8, 3, 20, 24) and int(out["pred_frames"].max()) == 0      # agreed failure, no hang in the gather
+    out = worker.do_some_tasks({**req, "return_objects": [True] * 3})                                   # and the worker keeps serving
+    ok &= int(out["pred_frames"][2].max()) == _expected(acts[2], 7)
     worker.serve_request(None)                                    # shutdown broadcast
     q.put((rank, bool(ok)))
     dist.destroy_process_group()

@@ -320,12 +320,19 @@ class ShardedWorldModelWorker(WorldModelWorker):
         if req is None:                                   # shutdown
             return None
         self.serial += 1
+        F, Ho, Wo = self.args.num_frames, self.args.out_height, self.args.out_width
+        dev = self.nav.device
+        n_req = len(req.get("save_dirs", [])) if isinstance(req, dict) else 0
+
+        def failed() -> dict:                             # the manager has no error channel: well-formed zero frames
+            zeros = np.zeros((n_req, F, 3, Ho, Wo), dtype=np.uint8)
+            return {"pred_frames": zeros, "save_dirs": list(req.get("save_dirs", [])) if isinstance(req, dict) else []}
+
+        ok, b, idx, loc, acts, small = True, 0, [], {}, None, None
         try:
             check_inputdict(req)
             assert name_matches(req["request_model_name"], WORLD_MODEL_NAME), f"request_model_name: {req['request_model_name']}"
             b, idx, loc = self._local(req)
-            dev = self.nav.device
-            F, Ho, Wo = self.args.num_frames, self.args.out_height, self.args.out_width
             if idx:
                 b_image = loc.get("b_image")
                 if b_image is None:
@@ -339,6 +346,15 @@ class ShardedWorldModelWorker(WorldModelWorker):
             else:
                 acts = np.zeros((0, F), np.int64)
                 small = torch.zeros((0, F, 3, Ho, Wo), dtype=torch.uint8, device=dev)
+        except Exception:
+            traceback.print_exc()
+            ok = False
+        # one rank failing must not leave the others waiting in the all-gather: agree on the outcome first (control plane, gloo)
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int32)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            return failed()
+        try:
             if bool(req.get("return_objects")):
                 out = gather_frames(small, b)                                  # the one data-path collective
                 return {"pred_frames": out.cpu().numpy(), "save_dirs": list(req["save_dirs"])} if self.rank == 0 else {}
@@ -348,9 +364,7 @@ class ShardedWorldModelWorker(WorldModelWorker):
             return {"save_dirs": list(req["save_dirs"])} if self.rank == 0 else {}
         except Exception:
             traceback.print_exc()
-            n = len(req.get("save_dirs", [])) if isinstance(req, dict) else 0
-            zeros = np.zeros((n, self.args.num_frames, 3, self.args.out_height, self.args.out_width), dtype=np.uint8)
-            return {"pred_frames": zeros, "save_dirs": list(req.get("save_dirs", []))}
+            return failed()
 
     def do_some_tasks(self, input_dict: dict) -> dict:            # rank 0's task_fn
         return self.serve_request(input_dict)
