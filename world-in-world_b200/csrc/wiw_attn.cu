@@ -501,8 +501,8 @@ extern "C" int wiw_attention_spatial(const void* qkv, void* out, int images, int
     // share of the exponentials evaluated on the FMA pipe instead of MUFU (development aid for A/B runs; see exp2_poly)
     static const int poly = getenv("WIW_ATTN_POLY") ? atoi(getenv("WIW_ATTN_POLY")) : 1;       // A/B on B200: 1 of 4 pairs on the FMA pipe = +6 % at S=9216; 2 of 4 = -4 %
     dim3 grid((S + 2 * kQ - 1) / (2 * kQ), C / 64, images);
-    // single-pass softmax (one TMEM sweep per KV tile): development aid for A/B runs, 0 = two-pass schedule
-    static const int onepass = getenv("WIW_ATTN_ONEPASS") ? atoi(getenv("WIW_ATTN_ONEPASS")) : 1;
+    // single-pass softmax (one TMEM sweep per KV tile, same results): measured slower than the two-pass schedule, kept for re-measurement
+    static const int onepass = getenv("WIW_ATTN_ONEPASS") ? atoi(getenv("WIW_ATTN_ONEPASS")) : 0;      // A/B on B200: -3.5 % (168 registers, less overlap): not the default
     if (onepass && poly == 1) attn_spatial_kernel<1, true><<<grid, kAttnThreads, kAttnSmem, stream>>>(tm_qkv, tm_out, a, C);
     else if (onepass && poly == 0) attn_spatial_kernel<0, true><<<grid, kAttnThreads, kAttnSmem, stream>>>(tm_qkv, tm_out, a, C);
     else if (poly == 1) attn_spatial_kernel<1, false><<<grid, kAttnThreads, kAttnSmem, stream>>>(tm_qkv, tm_out, a, C);
