@@ -156,6 +156,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--dump-gemm-profile", action="store_true")
+    ap.add_argument("--cfg-split", action="store_true",
+                    help="latency mode for fewer branches than GPUs (SURVEY 8f item 3): ranks (2k, 2k+1) share ONE branch, each "
+                         "running one row of the CFG pair with an all-gather of v per Euler step; N/2 branches in flight")
     ap.add_argument("--profiler-range", action="store_true",
                     help="cudaProfilerStart/Stop around the timed region (for `ncu --profile-from-start off`)")
     args = ap.parse_args()
@@ -197,9 +200,25 @@ def main():
     acts[0, 0] = 4
     aids = wm_worker.action_ids_idx_encode(acts)[0].float()
     gathered = torch.empty(world * F, 3, H, W, dtype=torch.uint8, device=dev) if world > 1 else None
+    pair_group = None
+    if args.cfg_split:
+        if world < 2 or world % 2:
+            raise SystemExit("--cfg-split needs an even number of GPUs")
+        for k in range(world // 2):                       # every rank creates every pair group (collective call)
+            grp = dist.new_group([2 * k, 2 * k + 1])
+            if rank // 2 == k:
+                pair_group = grp
+        # both ranks of a pair must hold the SAME branch: seed the inputs by pair index
+        g = torch.Generator(device=dev).manual_seed(100 + rank // 2)
+        lat0 = (torch.randn(F, 4, h, w, generator=g, device=dev, dtype=torch.float16) * sched.init_noise_sigma)
+        il = torch.randn(4, h, w, generator=g, device=dev, dtype=torch.float16)
+        ie = torch.randn(1, 1024, generator=g, device=dev, dtype=torch.float16)
+        acts = np.random.default_rng(3 + rank // 2).integers(1, 4, size=(1, F))
+        acts[0, 0] = 4
+        aids = wm_worker.action_ids_idx_encode(acts)[0].float()
 
     def step():
-        lat = ro.denoise(lat0, il, ie, aids, num_steps=N_STEPS)
+        lat = ro.denoise(lat0, il, ie, aids, num_steps=N_STEPS, cfg_split_group=pair_group)
         u8 = ro.decode(lat)
         if world > 1:
             dist.all_gather_into_tensor(gathered, u8)
@@ -233,7 +252,8 @@ def main():
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     total_ms = float(ms.item())
-    value = world * F * args.steps / (total_ms / 1e3)
+    branches = world // 2 if args.cfg_split else world
+    value = branches * F * args.steps / (total_ms / 1e3)
 
     # ---- stage split + roofline of the dominant kernel (conv_gemm_kernel), measured live on rank 0
     roof, stages = None, None
@@ -317,8 +337,11 @@ def main():
 
     if rank == 0:
         line = {"metric": METRIC, "value": round(value, 4), "unit": "frames/s", "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": round(total_ms / args.steps, 2), "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "f16", "data": "synthetic", "config": workload_config(world), "clocks": clocks,
+                "warmup": args.warmup, "ms_per_step": round(total_ms / args.steps, 2), "higher_is_better": True,
+                "scaling": "strong" if args.cfg_split else "weak",
+                "vs_baseline": None, "dtype": "f16", "data": "synthetic", "config": ({**workload_config(world), "branches": branches,
+                            "parallelism": f"cfg-split: {branches} branch(es), 2 GPUs per branch (one CFG row each), all-gather of v per Euler step"}
+                           if args.cfg_split else workload_config(world)), "clocks": clocks,
                 "e2e": e2e, "gpu_launches": launches, "roofline": roof, "stages": stages, "cpu_baseline": cpu_b}
         print(json.dumps(line), flush=True)
     if world > 1:

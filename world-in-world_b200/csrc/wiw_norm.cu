@@ -30,12 +30,8 @@ __device__ __forceinline__ void acc8(const uint4& u, float* s, float* q) {
 
 // ---------------------------------------------------------------- GroupNorm pass 1: partial sums
 // grid (chunks, samples); block = vpr * RL threads, thread (v, rl) owns channels [8v, 8v+8) and rows rl, rl+RL, ...
-// `counters` != nullptr: the LAST CTA of a sample to finish (ticket from an atomic counter that it resets afterwards) combines
-// the sample's partials -- in the same fixed order and fp64 arithmetic as gn_finalize_kernel -- so the separate finalize launch
-// (105 per UNet forward, 5-13 us each) disappears and the statistics stay bit-reproducible.
 __global__ void gn_stats_kernel(const __half* __restrict__ x, float* __restrict__ partial, long long rows_per_sample,
-                                int C, int G, int rows_per_chunk, int vpr, int RL,
-                                int* __restrict__ counters, float* __restrict__ stats, double count, float eps) {
+                                int C, int G, int rows_per_chunk, int vpr, int RL) {
     // smem: per-row-lane partials [RL][C] for sum and sumsq, then [C] column totals; fixed summation order
     // (no atomics) so the statistics -- and the whole rollout -- are bit-reproducible run to run
     extern __shared__ float sm[];
@@ -84,38 +80,6 @@ __global__ void gn_stats_kernel(const __half* __restrict__ x, float* __restrict_
         float* p = partial + (((long long)n * gridDim.x + chunk) * G + g) * 2;
         p[0] = a; p[1] = b;
     }
-    if (counters == nullptr) return;
-    __shared__ int s_last;
-    __threadfence();                                         // this CTA's partials are visible device-wide before its ticket
-    __syncthreads();
-    if (threadIdx.x == 0) s_last = (atomicAdd(&counters[n], 1) == (int)gridDim.x - 1);
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-    const int chunks = gridDim.x;
-    const int full_warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (warp < full_warps) {
-        for (int g = warp; g < G; g += full_warps) {
-            double a = 0.0, b = 0.0;
-            for (int k = lane; k < chunks; k += 32) {
-                const float2 pv = __ldcg(reinterpret_cast<const float2*>(partial + (((long long)n * chunks + k) * G + g) * 2));
-                a += (double)pv.x; b += (double)pv.y;
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                a += __shfl_xor_sync(0xffffffffu, a, o);
-                b += __shfl_xor_sync(0xffffffffu, b, o);
-            }
-            if (lane == 0) {
-                const double mean = a / count;
-                double var = b / count - mean * mean;
-                if (var < 0.0) var = 0.0;
-                stats[(n * G + g) * 2] = (float)mean;
-                stats[(n * G + g) * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
-            }
-        }
-    }
-    if (threadIdx.x == 0) counters[n] = 0;                   // ready for the next launch (stream order)
 }
 
 // ---------------------------------------------------------------- GroupNorm pass 1b: combine partials -> mean, rstd
@@ -711,8 +675,7 @@ gn_apply_stream_kernel(const __half* __restrict__ x, __half* __restrict__ y, con
 
 using namespace wiw;
 
-// partials | stats | one ticket counter per sample (must start zeroed; the kernels leave it zeroed)
-extern "C" int wiw_groupnorm_workspace_floats(int samples, int groups) { return samples * (kGnMaxChunks + 1) * groups * 2 + samples; }
+extern "C" int wiw_groupnorm_workspace_floats(int samples, int groups) { return samples * (kGnMaxChunks + 1) * groups * 2; }
 
 extern "C" int wiw_groupnorm(const void* x, void* y, int samples, long long rows_per_sample, int C, int G,
                              const float* gamma, const float* beta, float eps, int silu, float* workspace,
@@ -785,16 +748,12 @@ extern "C" int wiw_groupnorm(const void* x, void* y, int samples, long long rows
     };
     const long long rpc = pick_chunks(wavefit ? 2 * occ_s * num_sms() : 8 * num_sms());
     const int chunks = (int)((rows_per_sample + rpc - 1) / rpc);
-    static const int fuse_fin = getenv("WIW_GN_FUSEFIN") ? atoi(getenv("WIW_GN_FUSEFIN")) : 1;      // development aid for A/B runs
-    int* counters = reinterpret_cast<int*>(stats + (size_t)samples * G * 2);
     gn_stats_kernel<<<dim3(chunks, samples), threads, (size_t)(2 * RL + 2) * C * sizeof(float), stream>>>(
-        static_cast<const __half*>(x), partial, rows_per_sample, C, G, (int)rpc, vpr, RL, fuse_fin ? counters : nullptr, stats, count, eps);
+        static_cast<const __half*>(x), partial, rows_per_sample, C, G, (int)rpc, vpr, RL);
     WIW_CHECK_CUDA(cudaGetLastError());
-    if (!fuse_fin) {
-        const int warps = samples * G;
-        gn_finalize_kernel<<<(warps * 32 + 255) / 256, 256, 0, stream>>>(partial, stats, samples, G, chunks, count, eps);
-        WIW_CHECK_CUDA(cudaGetLastError());
-    }
+    const int warps = samples * G;
+    gn_finalize_kernel<<<(warps * 32 + 255) / 256, 256, 0, stream>>>(partial, stats, samples, G, chunks, count, eps);
+    WIW_CHECK_CUDA(cudaGetLastError());
     const long long arpc = pick_chunks(wavefit ? 4 * occ_a * num_sms() : 16 * num_sms());
     const int achunks = (int)((rows_per_sample + arpc - 1) / arpc);
     gn_apply_kernel<<<dim3(achunks, samples), threads, 0, stream>>>(

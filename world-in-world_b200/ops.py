@@ -296,7 +296,7 @@ def group_norm(x: torch.Tensor, nw: NormWeight, samples: int, eps: float, silu: 
     key = (x.device.index, torch.cuda.current_stream().cuda_stream)
     ws = _gn_ws.get(key)
     if ws is None or ws.numel() < need:
-        ws = torch.zeros(max(need, 1 << 16), dtype=torch.float32, device=x.device)      # ticket counters start at zero
+        ws = torch.empty(max(need, 1 << 16), dtype=torch.float32, device=x.device)
         _gn_ws[key] = ws
     L.check(lib.wiw_groupnorm(x.data_ptr(), out.data_ptr(), samples, rows, c, groups, nw.gamma.data_ptr(),
                               nw.beta.data_ptr(), float(eps), int(silu), ws.data_ptr(), L.stream_ptr()))

@@ -55,25 +55,51 @@ class Rollout:
     @torch.no_grad()
     def denoise(self, latents: torch.Tensor, image_latents: torch.Tensor, image_embedding: torch.Tensor,
                 action_ids: torch.Tensor, num_steps: int = 25, noise_aug_strength: float = 0.02,
-                min_guidance: float = 1.0, max_guidance: float = 3.0, trace: Optional[list] = None) -> torch.Tensor:
+                min_guidance: float = 1.0, max_guidance: float = 3.0, trace: Optional[list] = None,
+                cfg_split_group=None) -> torch.Tensor:
         """latents fp16 [F, 4, h, w] ALREADY scaled by init_noise_sigma (pipeline :359-361);
         image_latents [4, h, w]; image_embedding [1, D]; action_ids [F, A].
-        Returns the final latents, fp16 channels-last [F, h, w, 4]."""
+        Returns the final latents, fp16 channels-last [F, h, w, 4].
+
+        cfg_split_group: a 2-rank process group (intra-request parallelism when there are fewer
+        branches than GPUs).  The two rows of the classifier-free-guidance pair (pipeline :589-603) are independent UNet
+        samples: rank 0 of the group runs the unconditional row, rank 1 the conditional row (UNet batch 1 each), ONE
+        all-gather of v per Euler step ([F,h,w,32] fp16, 8 MB at 72x128) rebuilds the pair, and both ranks apply the same
+        (bit-exact) guidance + Euler update, so their latents stay identical without any further exchange."""
         lib = L.require_device()
         F = self.F
         _, _, h, w = latents.shape
         hw = h * w
         dev = self.device
         sched, steps, t_embs = self._schedule(num_steps)
-        self.unet.set_condition(image_embedding, noise_aug_strength, action_ids)
+        split_rank = -1
+        if cfg_split_group is not None:
+            import torch.distributed as dist
+            if dist.get_world_size(cfg_split_group) != 2:
+                raise ValueError("cfg_split_group must have exactly 2 ranks (unconditional row, conditional row)")
+            split_rank = dist.get_rank(cfg_split_group)
+            emb = image_embedding if split_rank == 1 else torch.zeros_like(image_embedding)      # CFG row 0 = zeros (pipeline :221-227)
+            self.unet.set_condition(emb, noise_aug_strength, action_ids, cfg_rows=False)
+        else:
+            self.unet.set_condition(image_embedding, noise_aug_strength, action_ids)
         lat = ops.nchw_to_nhwc(latents.to(dev, torch.float16).contiguous(), 4)                     # [F, h, w, 4]
         img = ops.nchw_to_nhwc(image_latents.to(dev, torch.float16).contiguous()[None], 4)[0]      # [h, w, 4]
         gs = torch.linspace(min_guidance, max_guidance, F).to(torch.float16).to(dev)               # pipeline :576-577
         x_in = torch.zeros(2 * F, h, w, 64, dtype=torch.float16, device=dev)
         st = L.stream_ptr
+        v_pair = None
         for i, sc in enumerate(steps):
             L.check(lib.wiw_sampler_prepare(lat.data_ptr(), img.data_ptr(), x_in.data_ptr(), F, hw, sc.div, st()))
-            v = (self.unet.forward_graphed if self.use_cuda_graph else self.unet.forward)(x_in, t_embs[i:i + 1])
+            if split_rank >= 0:
+                import torch.distributed as dist
+                v_half = (self.unet.forward_graphed if self.use_cuda_graph else self.unet.forward)(
+                    x_in[split_rank * F:(split_rank + 1) * F], t_embs[i:i + 1])
+                if v_pair is None:
+                    v_pair = torch.empty((2 * F,) + tuple(v_half.shape[1:]), dtype=v_half.dtype, device=dev)
+                dist.all_gather_into_tensor(v_pair, v_half.contiguous(), group=cfg_split_group)
+                v = v_pair
+            else:
+                v = (self.unet.forward_graphed if self.use_cuda_graph else self.unet.forward)(x_in, t_embs[i:i + 1])
             L.check(lib.wiw_sampler_step(v.data_ptr(), lat.data_ptr(), gs.data_ptr(), F, hw, v.shape[-1], sc.c_out,
                                          sc.sig2p1, sc.sigma, sc.dt, st()))
             if trace is not None:
