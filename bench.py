@@ -263,6 +263,8 @@ def main():
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record(); r = fn(); b.record(); torch.cuda.synchronize()
             return a.elapsed_time(b), r
+        if args.cfg_split:                                # the stage split below times the full CFG pair on one GPU
+            ro.unet.set_condition(ie, 0.02, aids)
         x_in = torch.zeros(2 * F, h, w, 64, dtype=torch.float16, device=dev)
         x_in[..., :8] = torch.randn(2 * F, h, w, 8, generator=g, device=dev, dtype=torch.float16)
         t_emb = sinusoid(sched.timesteps[:1], 320).to(torch.float16).to(dev)

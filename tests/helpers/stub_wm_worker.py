@@ -2,7 +2,7 @@
 WorldModelWorker.do_some_tasks -- around a fake Navigator that needs no GPU.  Spawned by
 tests/test_reference_manager_interop_cpu.py through the reference's own manager code, exactly as a genex worker
 would be (`<python> <script> <flags...> <w_fd>`).  Frame content encodes the request so the test can check routing:
-pixel value of frame t of a branch = (sum(actions) * 7 + t) % 256."""
+pixel value of frame t of a branch = (sum(actions) * 7 + t) % 256 (+100 when the branch ran as a CFG pair)."""
 import os
 import sys
 
@@ -20,7 +20,8 @@ class FakeNavigator:
         self.args = args
         self.device = torch.device("cpu")
 
-    def inference(self, actions, images_u8, out_width=None, out_height=None, latents=None, on_device=False, seeds=None):
+    def inference(self, actions, images_u8, out_width=None, out_height=None, latents=None, on_device=False, seeds=None,
+                  cfg_split_group=None):
         b, F = actions.shape[0], self.args.num_frames
         assert images_u8.shape[1] in (3, 4) and images_u8.dtype == np.uint8
         acts = torch.diagonal(actions, dim1=-2, dim2=-1)
@@ -29,7 +30,7 @@ class FakeNavigator:
             if int(acts[i].sum()) == 77:
                 raise RuntimeError("stub: injected failure for this branch")
             for t in range(F):
-                out[i, t] = int((int(acts[i].sum()) * 7 + t) % 256)
+                out[i, t] = int((int(acts[i].sum()) * 7 + t + (100 if cfg_split_group is not None else 0)) % 256)
         return out
 
 

@@ -76,3 +76,42 @@ def test_sharded_worker_world2(tmp_path):
     res = [q.get(timeout=180) for _ in ps]
     [p.join(60) for p in ps]
     assert all(ok for _, ok in res), res
+
+
+def _run_pairs(rank, world, port, tmp, q):
+    sys.path.insert(0, HELPERS)
+    import stub_wm_worker as S
+    from wiw_b200 import wm_worker as W
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    args = W.build_parser().parse_args(["--width", "64", "--height", "32", "--out_width", "24", "--out_height", "20", "--num_frames", "8",
+                                        "--action_input_channel", "8", "--gpus", str(world), "--rank", str(rank), "--cfg_split"])
+    worker = W.ShardedWorldModelWorker(args, S.FakeNavigator(args), rank, world)
+    worker._resizer_key = (args.height, args.width, args.out_height, args.out_width)
+    worker._resizer = S.cpu_resizer(args)
+    if rank > 0:
+        worker.helper_loop()
+        q.put((rank, True))
+        dist.destroy_process_group()
+        return
+    ok = worker.pair_group is not None
+    acts = np.array([[4, 1, 2, 2, 1, 3, 1, 1], [1, 3, 3, 1, 1, 1, 2, 0], [2, 2, 2, 2, 1, 1, 1, 1]], dtype=np.int64)
+    for b, paired in ((2, True), (1, True), (3, False)):            # 2*b <= 4 ranks -> CFG pairs; 3 branches -> one branch per rank
+        req = {"b_action": acts[:b], "b_image": np.zeros((b, 3, 32, 64), np.uint8), "save_dirs": [os.path.join(tmp, f"p{b}_{i}") for i in range(b)],
+               "request_model_name": "igen", "return_objects": [True] * b}
+        pf = worker.do_some_tasks(req)["pred_frames"]
+        ok &= pf.shape == (b, 8, 3, 20, 24)
+        bump = 100 if paired else 0
+        ok &= all(int(pf[i, t].min()) == int(pf[i, t].max()) == (_expected(acts[i], t) + bump) % 256 for i in range(b) for t in range(8))
+    worker.serve_request(None)
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_sharded_worker_cfg_pairs_world4(tmp_path):
+    ctx = mp.get_context("spawn")
+    q, port = ctx.Queue(), _free_port()
+    ps = [ctx.Process(target=_run_pairs, args=(r, 4, port, str(tmp_path), q)) for r in range(4)]
+    [p.start() for p in ps]
+    res = [q.get(timeout=180) for _ in ps]
+    [p.join(60) for p in ps]
+    assert all(ok for _, ok in res), res

@@ -42,3 +42,34 @@ def gather_frames(local: torch.Tensor, b: int, group=None) -> torch.Tensor:
         if idx:
             res[idx] = out[r * m: r * m + len(idx)]
     return res
+
+
+# ----------------------------------------------------------------------------- CFG-split pairs (fewer branches than GPUs)
+def pair_layout(b: int, world: int):
+    """Branch placement when the R ranks work as R/2 CFG pairs (ranks 2p, 2p+1 run the two rows of ONE branch's guidance pair,
+    SURVEY.md section 8f item 3): branch i -> pair i % P.  Returns (pairs, owner) with owner[i] = (leader rank, local position)."""
+    pairs = world // 2
+    owner = [(2 * (i % pairs), i // pairs) for i in range(b)]
+    return pairs, owner
+
+
+def pair_branch_indices(b: int, rank: int, world: int) -> List[int]:
+    pairs = world // 2
+    return list(range(rank // 2, b, pairs))
+
+
+def gather_frames_pairs(local: torch.Tensor, b: int, group=None) -> torch.Tensor:
+    """Like gather_frames for the pair layout: every rank contributes its (zero-padded) block in ONE all-gather, the pair
+    leaders' blocks are the ones read back.  local uint8 [b_local, ...] in pair_branch_indices order."""
+    world = dist.get_world_size(group)
+    pairs, owner = pair_layout(b, world)
+    m = (b + pairs - 1) // pairs
+    shape = tuple(local.shape[1:])
+    block = torch.zeros((m,) + shape, dtype=local.dtype, device=local.device)
+    block[: local.shape[0]] = local
+    out = torch.empty((world * m,) + shape, dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, block, group=group)
+    res = torch.empty((b,) + shape, dtype=local.dtype, device=local.device)
+    for i, (leader, pos) in enumerate(owner):
+        res[i] = out[leader * m + pos]
+    return res
