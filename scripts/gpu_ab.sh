@@ -1,30 +1,27 @@
 #!/bin/bash
-# One gpurun call for an A/B round: validate the new kernel variants first, fall back per feature if a parity test
-# fails, time old vs new in the same box, then run the full GPU suite and the bench with the chosen variants.
-#   gpurun --timeout 1200 -- 'bash scripts/gpu_ab.sh'
+# Same-box A/B of one development switch (boxes of the pod differ by ~5 %, so a change is only accepted on a pair measured
+# back to back in ONE gpurun call):
+#   gpurun --timeout 900 -- 'bash scripts/gpu_ab.sh WIW_GELU 1 2 "tests/test_gemm_gpu.py -k geglu" "scripts/perf_gemm.py geglu"'
+# 1. parity tests with VAR=NEW (on failure everything after runs with OLD only), 2. the micro-benchmark with OLD and NEW side by side,
+# 3. model parity tests (margins land in gpurun_out/parity.jsonl), 4. bench with NEW then OLD (device-timed value only).
 set -u
+VAR=$1; OLD=$2; NEW=$3; TESTS=${4:-}; PERF=${5:-}
 mkdir -p gpurun_out
 cd "$(dirname "$0")/.."
-export NORM_V=2 GEMM_EPI=1
-timeout 300 python -m pytest tests/test_kernels_gpu.py -x -q -k "groupnorm or layernorm" > gpurun_out/t_norm.log 2>&1 || NORM_V=1
-echo "norm tests -> WIW_NORM_V=$NORM_V"; tail -3 gpurun_out/t_norm.log
-timeout 300 python -m pytest tests/test_gemm_gpu.py -x -q > gpurun_out/t_gemm.log 2>&1 || GEMM_EPI=0
-echo "gemm tests -> WIW_GEMM_EPI=$GEMM_EPI"; tail -3 gpurun_out/t_gemm.log
-
-WIW_GEMM_EPI=0 timeout 200 python scripts/perf_gemm.py > gpurun_out/perf_gemm_epi0.log 2>&1; echo "perf_gemm epi0 exit $?"
-if [ "$GEMM_EPI" = 1 ]; then
-    WIW_GEMM_EPI=1 timeout 200 python scripts/perf_gemm.py > gpurun_out/perf_gemm_epi1.log 2>&1; echo "perf_gemm epi1 exit $?"
+rm -f gpurun_out/parity.jsonl
+USE=$NEW
+if [ -n "$TESTS" ]; then
+    env $VAR=$NEW timeout 300 python -m pytest $TESTS -x -q > gpurun_out/ab_tests.log 2>&1 || USE=$OLD
+    echo "parity tests with $VAR=$NEW -> using $VAR=$USE"; tail -3 gpurun_out/ab_tests.log
 fi
-WIW_NORM_V=1 timeout 200 python scripts/perf_attn.py norm > gpurun_out/perf_norm_v1.log 2>&1; echo "perf_norm v1 exit $?"
-if [ "$NORM_V" = 2 ]; then
-    WIW_NORM_V=2 timeout 200 python scripts/perf_attn.py norm > gpurun_out/perf_norm_v2.log 2>&1; echo "perf_norm v2 exit $?"
+if [ -n "$PERF" ]; then
+    for v in $OLD $NEW; do env $VAR=$v timeout 200 python $PERF > gpurun_out/ab_perf_$v.log 2>&1; done
+    paste -d'|' gpurun_out/ab_perf_$OLD.log gpurun_out/ab_perf_$NEW.log | cut -c1-230
 fi
-paste -d'|' gpurun_out/perf_gemm_epi0.log gpurun_out/perf_gemm_epi1.log 2>/dev/null | cut -c1-230
-paste -d'|' gpurun_out/perf_norm_v1.log gpurun_out/perf_norm_v2.log 2>/dev/null | cut -c1-200
-
-export WIW_NORM_V=$NORM_V WIW_GEMM_EPI=$GEMM_EPI
-timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/tests_gpu.log 2>&1
-echo "tests exit $?"; tail -4 gpurun_out/tests_gpu.log
-timeout 600 python bench.py --steps 2 --warmup 3 > gpurun_out/bench.log 2> gpurun_out/bench.err
-echo "bench exit $?"; tail -1 gpurun_out/bench.log
+env $VAR=$USE timeout 400 python -m pytest tests/test_model_full_gpu.py tests/test_model_gpu.py -x -q > gpurun_out/ab_model.log 2>&1
+echo "model tests ($VAR=$USE) exit $?"; cat gpurun_out/parity.jsonl
+env $VAR=$USE timeout 600 python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/bench.log 2> gpurun_out/bench.err
+echo "bench $VAR=$USE exit $?"; tail -1 gpurun_out/bench.log | cut -c1-200
+env $VAR=$OLD timeout 600 python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/bench_prev_settings.log 2>> gpurun_out/bench.err
+echo "bench $VAR=$OLD exit $?"; tail -1 gpurun_out/bench_prev_settings.log | cut -c1-200
 echo session done

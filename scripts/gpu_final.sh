@@ -11,7 +11,7 @@ timeout 600 python bench.py --steps 3 --warmup 3 --dump-gemm-profile > gpurun_ou
 echo "bench exit $?"; tail -1 gpurun_out/bench.log
 timeout 300 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.log 2>> gpurun_out/bench.err
 echo "bench ref exit $?"; tail -1 gpurun_out/bench_ref.log | cut -c1-200
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:wiw --csv --log-file gpurun_out/launches_unet.csv \
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'conv_gemm|attn_spatial|temporal_attn|gn_|layernorm|concat_kernel|upsample2x|emb_silu' --csv --log-file gpurun_out/launches_unet.csv \
     python scripts/ncu_unet.py 2 > gpurun_out/launches_unet.log 2>&1
 echo "launch list exit $?"; wc -l gpurun_out/launches_unet.csv
 timeout 400 ncu --set full --clock-control none --import-source on -k regex:'conv_gemm|attn_spatial' -o gpurun_out/full_kernels -f \

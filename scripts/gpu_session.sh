@@ -26,8 +26,10 @@ if has perf; then
     true
 fi
 if has launches; then
-    # launch list of the SAME command as the bench (one timed step: 25 UNet forwards + decode), timed region only
-    timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv \
+    # launch list of the SAME command as the bench, timed region only.  ncu walks every kernel node of the replayed CUDA graphs
+    # at ~5 launches/s: a whole clip (14.5 k launches) does not fit a sensible budget, so the list is capped at two Euler steps
+    # (-c 1500); scripts/gpu_final.sh lists one eager UNet forward instead, which takes 30 s.
+    timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off -c 1500 --csv \
         --log-file gpurun_out/launches_bench.csv \
         python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu-baseline --profiler-range > gpurun_out/launches_bench.log 2>&1
     echo "launches exit $?"; wc -l gpurun_out/launches_bench.csv

@@ -93,22 +93,7 @@ __device__ __forceinline__ void exp_chunk(const uint32_t* r, int ch, float c, fl
     }
 }
 
-// 32 scores -> 16 packed fp16x2 probabilities kept in registers (single-pass softmax: stored once PV of the previous tile retired)
-template <int kPolyPairs>
-__device__ __forceinline__ void exp_chunk_regs(const uint32_t* r, float c, float mc, uint32_t* out16) {
-#pragma unroll
-    for (int v8 = 0; v8 < 4; ++v8) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const float a0 = fmaf(__uint_as_float(r[v8 * 8 + 2 * e]), c, -mc);
-            const float a1 = fmaf(__uint_as_float(r[v8 * 8 + 2 * e + 1]), c, -mc);
-            if (e < kPolyPairs) out16[v8 * 4 + e] = cvt_f16x2(exp2_poly(a0), exp2_poly(a1));
-            else out16[v8 * 4 + e] = cvt_f16x2(fast_exp2(a0), fast_exp2(a1));
-        }
-    }
-}
-
-template <int POLY, bool ONEPASS>
+template <int POLY>
 __global__ void __launch_bounds__(kAttnThreads, 1)
 attn_spatial_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_out,
                     const __grid_constant__ AttnArgs a, int C) {
@@ -256,81 +241,6 @@ attn_spatial_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
             const bool masked = valid < kKV;
             mbar_wait(bar_s_full + 8 * t, (uint32_t)j & 1u);
             tc_fence_after();
-            if (ONEPASS && !masked && j > 0) {
-                // ---- single pass over S_t: exponentials against the CURRENT reference maximum and the new row maximum in the same
-                // sweep (TMEM is read once, not twice), probabilities held in 64 registers while PV of the previous tile still owns
-                // the P buffer.  Only if some row maximum of the warp grew by more than 2^8 (rare after the first tiles) the sweep is
-                // repeated with the updated reference -- the result is identical to the two-pass schedule.
-                uint32_t preg[64];
-                float mx1 = -INFINITY;
-                float mc1 = m_ref * c;
-                {
-                    uint32_t ra[32], rb[32];
-                    tmem_ld_32x32b_x32(tS, ra);
-                    tmem_ld_wait();
-                    tmem_ld_32x32b_x32(tS + 32, rb);
-                    mx1 = row_max_chunk(ra, mx1);
-                    exp_chunk_regs<POLY>(ra, c, mc1, preg);
-                    tmem_ld_wait();
-                    tmem_ld_32x32b_x32(tS + 64, ra);
-                    mx1 = row_max_chunk(rb, mx1);
-                    exp_chunk_regs<POLY>(rb, c, mc1, preg + 16);
-                    tmem_ld_wait();
-                    tmem_ld_32x32b_x32(tS + 96, rb);
-                    mx1 = row_max_chunk(ra, mx1);
-                    exp_chunk_regs<POLY>(ra, c, mc1, preg + 32);
-                    tmem_ld_wait();
-                    mx1 = row_max_chunk(rb, mx1);
-                    exp_chunk_regs<POLY>(rb, c, mc1, preg + 48);
-                }
-                float alpha1 = 1.f;
-                const bool grow1 = (mx1 - m_ref) * c > kRescaleThreshold;
-                const bool any_grow1 = __any_sync(0xffffffffu, grow1);
-                if (any_grow1) {
-                    const float m_new = fmaxf(m_ref, mx1);
-                    alpha1 = fast_exp2((m_ref - m_new) * c);
-                    m_ref = m_new;
-                    mc1 = m_ref * c;
-#pragma unroll
-                    for (int ch = 0; ch < 4; ++ch) {              // S_t is still ours: redo the exponentials against the new reference
-                        uint32_t r[32];
-                        tmem_ld_32x32b_x32(tS + ch * 32, r);
-                        tmem_ld_wait();
-                        exp_chunk_regs<POLY>(r, c, mc1, preg + ch * 16);
-                    }
-                }
-                tc_fence_before();                               // last read of S_t: release it for the next QK
-                mbar_arrive(bar_s_free + 8 * t);
-                // the P_t buffer and O_t belong to the tensor core until PV of tile j-1 has retired
-                mbar_wait(bar_pv_done + 8 * t, (uint32_t)(j - 1) & 1u);
-                tc_fence_after();
-                if (any_grow1) {
-#pragma unroll
-                    for (int ch = 0; ch < kOCols / 16; ++ch) {
-                        uint32_t r[16];
-                        tmem_ld_32x32b_x16(tO + ch * 16, r);
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int e = 0; e < 16; ++e) r[e] = __float_as_uint(__uint_as_float(r[e]) * alpha1);
-                        tmem_st_32x32b_x16(tO + ch * 16, r);
-                    }
-                    tmem_st_wait();
-                }
-#pragma unroll
-                for (int ch = 0; ch < 4; ++ch) {
-                    uint8_t* dst = pP + (ch >> 1) * kTileBytes;
-#pragma unroll
-                    for (int v8 = 0; v8 < 4; ++v8) {
-                        const uint32_t chunk16 = (uint32_t)((ch & 1) * 4 + v8);
-                        *reinterpret_cast<uint4*>(dst + ((chunk16 ^ sw) << 4)) =
-                            make_uint4(preg[ch * 16 + v8 * 4], preg[ch * 16 + v8 * 4 + 1], preg[ch * 16 + v8 * 4 + 2], preg[ch * 16 + v8 * 4 + 3]);
-                    }
-                }
-                fence_proxy_async_smem();
-                tc_fence_before();
-                mbar_arrive(bar_p_full + 8 * t);
-                continue;
-            }
             // pass 1: row max.  The TMEM load of chunk ch+1 is in flight while chunk ch is reduced.
             float mx = -INFINITY;
             if (!masked) {
@@ -491,23 +401,19 @@ extern "C" int wiw_attention_spatial(const void* qkv, void* out, int images, int
     a.scale_log2 = 0.125f * 1.4426950408889634f;
     static bool attr_set = false;
     if (!attr_set) {
-        WIW_CHECK_CUDA(cudaFuncSetAttribute(attn_spatial_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
-        WIW_CHECK_CUDA(cudaFuncSetAttribute(attn_spatial_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
-        WIW_CHECK_CUDA(cudaFuncSetAttribute(attn_spatial_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
-        WIW_CHECK_CUDA(cudaFuncSetAttribute(attn_spatial_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
-        WIW_CHECK_CUDA(cudaFuncSetAttribute(attn_spatial_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
+        WIW_CHECK_CUDA(cudaFuncSetAttribute(attn_spatial_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
+        WIW_CHECK_CUDA(cudaFuncSetAttribute(attn_spatial_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
+        WIW_CHECK_CUDA(cudaFuncSetAttribute(attn_spatial_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
         attr_set = true;
     }
     // share of the exponentials evaluated on the FMA pipe instead of MUFU (development aid for A/B runs; see exp2_poly)
     static const int poly = getenv("WIW_ATTN_POLY") ? atoi(getenv("WIW_ATTN_POLY")) : 1;       // A/B on B200: 1 of 4 pairs on the FMA pipe = +6 % at S=9216; 2 of 4 = -4 %
     dim3 grid((S + 2 * kQ - 1) / (2 * kQ), C / 64, images);
-    // single-pass softmax (one TMEM sweep per KV tile, same results): measured slower than the two-pass schedule, kept for re-measurement
-    static const int onepass = getenv("WIW_ATTN_ONEPASS") ? atoi(getenv("WIW_ATTN_ONEPASS")) : 0;      // A/B on B200: -3.5 % (168 registers, less overlap): not the default
-    if (onepass && poly == 1) attn_spatial_kernel<1, true><<<grid, kAttnThreads, kAttnSmem, stream>>>(tm_qkv, tm_out, a, C);
-    else if (onepass && poly == 0) attn_spatial_kernel<0, true><<<grid, kAttnThreads, kAttnSmem, stream>>>(tm_qkv, tm_out, a, C);
-    else if (poly == 1) attn_spatial_kernel<1, false><<<grid, kAttnThreads, kAttnSmem, stream>>>(tm_qkv, tm_out, a, C);
-    else if (poly == 2) attn_spatial_kernel<2, false><<<grid, kAttnThreads, kAttnSmem, stream>>>(tm_qkv, tm_out, a, C);
-    else attn_spatial_kernel<0, false><<<grid, kAttnThreads, kAttnSmem, stream>>>(tm_qkv, tm_out, a, C);
+    // (a single-pass softmax variant -- one TMEM sweep per KV tile, probabilities parked in registers -- gave the same results
+    // 3.5 % slower on B200 and was removed again: DESIGN.md section 4, profiles/r01_perf_attn_onepass_ab_v9.txt)
+    if (poly == 1) attn_spatial_kernel<1><<<grid, kAttnThreads, kAttnSmem, stream>>>(tm_qkv, tm_out, a, C);
+    else if (poly == 2) attn_spatial_kernel<2><<<grid, kAttnThreads, kAttnSmem, stream>>>(tm_qkv, tm_out, a, C);
+    else attn_spatial_kernel<0><<<grid, kAttnThreads, kAttnSmem, stream>>>(tm_qkv, tm_out, a, C);
     WIW_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

@@ -357,320 +357,6 @@ layernorm_lpr_kernel(const __half* __restrict__ x, __half* __restrict__ y, const
     }
 }
 
-// ================================================================================================
-// TMA-fed streaming variants (default).  The register-staged kernels above keep only
-// (threads x unroll x 16 B) in flight and stop loading while they compute, which holds them at ~45 % of the HBM
-// rate (profiles/r01_perf_attn_norm_v5.txt).  Here one producer warp streams contiguous row tiles into a 4-stage
-// shared-memory ring with cp.async.bulk (1-D TMA, completion on an mbarrier); the consumer warps read rows from
-// shared memory, so 3 tiles (~45-60 KB) per CTA are in flight all the time, independent of register pressure.
-// ================================================================================================
-constexpr int kRing = 4;
-
-__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(bar) : "memory");
-}
-
-// Producer warp: rows [0, nrows) starting at `src` (row-major, row_bytes each) go through the ring in tiles of tile_rows.
-__device__ __forceinline__ void ring_produce(const uint8_t* src, long long nrows, int tile_rows, uint32_t row_bytes, uint32_t ring,
-                                             uint32_t tile_bytes, uint32_t bar_full, uint32_t bar_empty) {
-    int s = 0;
-    uint32_t ph = 0;
-    for (long long r = 0; r < nrows; r += tile_rows) {
-        const long long left = nrows - r;
-        const uint32_t rows = left < tile_rows ? (uint32_t)left : (uint32_t)tile_rows;
-        mbar_wait(bar_empty + 8 * s, ph ^ 1);
-        if (elect_one()) {
-            const uint32_t bytes = rows * row_bytes;
-            mbar_expect_tx(bar_full + 8 * s, bytes);
-            bulk_load_1d(ring + s * tile_bytes, src + r * row_bytes, bytes, bar_full + 8 * s);
-        }
-        __syncwarp();
-        if (++s == kRing) { s = 0; ph ^= 1; }
-    }
-}
-
-__device__ __forceinline__ void ring_init(uint32_t bar_full, uint32_t bar_empty, uint32_t consumer_warps) {
-    if (threadIdx.x == 0) {
-        for (int i = 0; i < kRing; ++i) {
-            mbar_init(bar_full + 8 * i, 1);
-            mbar_init(bar_empty + 8 * i, consumer_warps);
-        }
-        fence_barrier_init();
-    }
-    __syncthreads();
-}
-
-// ---------------------------------------------------------------- LayerNorm, streaming
-// block = 8 consumer warps + 1 producer warp; a CTA owns rows [blockIdx.x * rows_per_cta, ...); tile = 8 * RPW rows,
-// consumer warp w normalises rows w, w + 8, ... of each tile.  gamma / beta of a lane's channels live in registers.
-template <int VPL, int RPW>
-__global__ void __launch_bounds__(288, (VPL <= 2) ? 2 : 1)
-layernorm_stream_kernel(const __half* __restrict__ x, __half* __restrict__ y, const float* __restrict__ gamma,
-                        const float* __restrict__ beta, const __half* __restrict__ tab, int tab_div, int tab_mod,
-                        long long M, int C, float eps, long long rows_per_cta) {
-    extern __shared__ __align__(128) uint8_t smem_ln[];
-    const uint32_t row_bytes = (uint32_t)C * 2u;
-    const int tile_rows = 8 * RPW;
-    const uint32_t tile_bytes = (uint32_t)tile_rows * row_bytes;
-    const uint32_t ring = smem_u32(smem_ln);
-    const uint32_t bar_full = ring + kRing * tile_bytes, bar_empty = bar_full + 8 * kRing;
-    const long long r0 = (long long)blockIdx.x * rows_per_cta;
-    long long nrows = M - r0;
-    if (nrows > rows_per_cta) nrows = rows_per_cta;
-    if (nrows <= 0) return;
-    ring_init(bar_full, bar_empty, 8);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (warp == 8) {
-        ring_produce(reinterpret_cast<const uint8_t*>(x + r0 * C), nrows, tile_rows, row_bytes, ring, tile_bytes, bar_full, bar_empty);
-        return;
-    }
-    const int nvec = C >> 3;
-    constexpr bool kRegAffine = VPL <= 5;        // wider rows re-read gamma / beta from L1 instead (register budget)
-    constexpr int GV = kRegAffine ? VPL : 1;
-    float gg[GV][8], bb[GV][8];
-    if (kRegAffine) {
-#pragma unroll
-        for (int i = 0; i < GV; ++i) {
-            const int vi = lane + 32 * i;
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                gg[i][e] = (vi < nvec) ? gamma[vi * 8 + e] : 0.f;
-                bb[i][e] = (vi < nvec) ? beta[vi * 8 + e] : 0.f;
-            }
-        }
-    }
-    const float inv_c = 1.0f / (float)C;
-    int s = 0;
-    uint32_t ph = 0;
-    for (long long r = 0; r < nrows; r += tile_rows) {
-        const long long left = nrows - r;
-        const int rows = left < tile_rows ? (int)left : tile_rows;
-        mbar_wait(bar_full + 8 * s, ph);
-        const uint8_t* tile = smem_ln + (size_t)s * tile_bytes;
-        uint4 raw[RPW][VPL];
-#pragma unroll
-        for (int k = 0; k < RPW; ++k) {
-            const int lr = warp + 8 * k;
-#pragma unroll
-            for (int i = 0; i < VPL; ++i) {
-                const int vi = lane + 32 * i;
-                raw[k][i] = (vi < nvec && lr < rows) ? *reinterpret_cast<const uint4*>(tile + (size_t)lr * row_bytes + vi * 16)
-                                                     : make_uint4(0, 0, 0, 0);
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < RPW; ++k) {
-            const int lr = warp + 8 * k;
-            if (lr >= rows) break;
-            const long long row = r0 + r + lr;
-            float v[VPL][8];
-            const __half* trow = tab ? tab + (size_t)((row / tab_div) % tab_mod) * C : nullptr;
-            float sum = 0.f;
-#pragma unroll
-            for (int i = 0; i < VPL; ++i) {
-                const int vi = lane + 32 * i;
-                const __half2* h = reinterpret_cast<const __half2*>(&raw[k][i]);
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const float2 f = __half22float2(h[e]);
-                    v[i][2 * e] = f.x; v[i][2 * e + 1] = f.y;
-                }
-                if (trow && vi < nvec) {
-                    const uint4 tu = __ldg(reinterpret_cast<const uint4*>(trow + vi * 8));
-                    const __half2* th = reinterpret_cast<const __half2*>(&tu);
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        // the reference adds in fp16 (hidden_states + emb, transformer_temporal.py:360)
-                        const float2 tf = __half22float2(th[e]);
-                        v[i][2 * e] = __half2float(__float2half_rn(v[i][2 * e] + tf.x));
-                        v[i][2 * e + 1] = __half2float(__float2half_rn(v[i][2 * e + 1] + tf.y));
-                    }
-                }
-#pragma unroll
-                for (int e = 0; e < 8; ++e) sum += v[i][e];       // lanes beyond nvec hold zeros
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-            const float mean = sum * inv_c;
-            float sq = 0.f;
-#pragma unroll
-            for (int i = 0; i < VPL; ++i) {
-                if (lane + 32 * i < nvec) {
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) { const float d = v[i][e] - mean; sq += d * d; }
-                }
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-            const float rstd = rsqrtf(sq * inv_c + eps);
-#pragma unroll
-            for (int i = 0; i < VPL; ++i) {
-                const int vi = lane + 32 * i;
-                if (vi < nvec) {
-                    float ge[8], be[8];
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        ge[e] = kRegAffine ? gg[kRegAffine ? i : 0][e] : __ldg(gamma + vi * 8 + e);
-                        be[e] = kRegAffine ? bb[kRegAffine ? i : 0][e] : __ldg(beta + vi * 8 + e);
-                    }
-                    uint4 o;
-                    __half2* oh = reinterpret_cast<__half2*>(&o);
-#pragma unroll
-                    for (int e = 0; e < 4; ++e)
-                        oh[e] = __floats2half2_rn((v[i][2 * e] - mean) * rstd * ge[2 * e] + be[2 * e],
-                                                  (v[i][2 * e + 1] - mean) * rstd * ge[2 * e + 1] + be[2 * e + 1]);
-                    *reinterpret_cast<uint4*>(y + row * C + vi * 8) = o;
-                }
-            }
-        }
-        // Release the stage only after the loaded registers were consumed: an LDS is complete once its destination has
-        // been read, not when it was issued (an arrive right after issuing the loads raced with the next TMA write).
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_empty + 8 * s);
-        if (++s == kRing) { s = 0; ph ^= 1; }
-    }
-}
-
-// ---------------------------------------------------------------- GroupNorm, streaming
-// Same (chunk, sample) grid and (v, rl) thread mapping as the kernels above -- thread (v, rl) owns channels [8v, 8v+8) of
-// rows rl, rl + RL, ... -- so the partial sums are accumulated in the same fixed order; tile = 4 * RL rows.
-constexpr int kGnKU = 4;
-
-__global__ void __launch_bounds__(288, 2)
-gn_stats_stream_kernel(const __half* __restrict__ x, float* __restrict__ partial, long long rows_per_sample, int C, int G,
-                       long long rows_per_chunk, int vpr, int RL, int consumer_warps) {
-    extern __shared__ __align__(128) uint8_t smem_gs[];
-    const uint32_t row_bytes = (uint32_t)C * 2u;
-    const int tile_rows = kGnKU * RL;
-    const uint32_t tile_bytes = (uint32_t)tile_rows * row_bytes;
-    const uint32_t ring = smem_u32(smem_gs);
-    const uint32_t bar_full = ring + kRing * tile_bytes, bar_empty = bar_full + 8 * kRing;
-    float* red = reinterpret_cast<float*>(smem_gs + (size_t)kRing * tile_bytes + 128);      // [(2 RL + 2)][C]
-    const int chunk = blockIdx.x, n = blockIdx.y;
-    const long long r0 = (long long)chunk * rows_per_chunk;
-    long long nrows = rows_per_sample - r0;
-    if (nrows > rows_per_chunk) nrows = rows_per_chunk;
-    ring_init(bar_full, bar_empty, consumer_warps);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int T = vpr * RL;
-    if (warp == consumer_warps) {
-        if (nrows > 0)
-            ring_produce(reinterpret_cast<const uint8_t*>(x + ((long long)n * rows_per_sample + r0) * C), nrows, tile_rows, row_bytes,
-                         ring, tile_bytes, bar_full, bar_empty);
-    } else {
-        const bool active = (int)threadIdx.x < T;
-        const int v = threadIdx.x % vpr, rl = threadIdx.x / vpr;
-        float s[8], q[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) { s[e] = 0.f; q[e] = 0.f; }
-        int st = 0;
-        uint32_t ph = 0;
-        for (long long r = 0; r < nrows; r += tile_rows) {
-            const long long left = nrows - r;
-            const int rows = left < tile_rows ? (int)left : tile_rows;
-            mbar_wait(bar_full + 8 * st, ph);
-            const uint8_t* tile = smem_gs + (size_t)st * tile_bytes;
-            uint4 u[kGnKU];
-#pragma unroll
-            for (int k = 0; k < kGnKU; ++k) {
-                const int lr = k * RL + rl;
-                u[k] = (active && lr < rows) ? *reinterpret_cast<const uint4*>(tile + (size_t)lr * row_bytes + v * 16) : make_uint4(0, 0, 0, 0);
-            }
-#pragma unroll
-            for (int k = 0; k < kGnKU; ++k) acc8(u[k], s, q);          // padded rows add zeros
-            __syncwarp();                                              // loads consumed -> the stage may be overwritten
-            if (lane == 0) mbar_arrive(bar_empty + 8 * st);
-            if (++st == kRing) { st = 0; ph ^= 1; }
-        }
-        if (active) {
-            float* p_sum = red;
-            float* p_sq = red + (size_t)RL * C;
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                p_sum[rl * C + v * 8 + e] = s[e];
-                p_sq[rl * C + v * 8 + e] = q[e];
-            }
-        }
-    }
-    __syncthreads();
-    float* p_sum = red;
-    float* p_sq = red + (size_t)RL * C;
-    float* s_sum = p_sq + (size_t)RL * C;
-    float* s_sq = s_sum + C;
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        float a = 0.f, b = 0.f;
-        for (int k = 0; k < RL; ++k) { a += p_sum[k * C + c]; b += p_sq[k * C + c]; }
-        s_sum[c] = a; s_sq[c] = b;
-    }
-    __syncthreads();
-    const int cg = C / G;
-    for (int g = threadIdx.x; g < G; g += blockDim.x) {
-        float a = 0.f, b = 0.f;
-        for (int c = 0; c < cg; ++c) { a += s_sum[g * cg + c]; b += s_sq[g * cg + c]; }
-        float* p = partial + (((long long)n * gridDim.x + chunk) * G + g) * 2;
-        p[0] = a; p[1] = b;
-    }
-}
-
-__global__ void __launch_bounds__(288, 2)
-gn_apply_stream_kernel(const __half* __restrict__ x, __half* __restrict__ y, const float* __restrict__ stats,
-                       const float* __restrict__ gamma, const float* __restrict__ beta, long long rows_per_sample, int C, int G,
-                       long long rows_per_chunk, int vpr, int RL, int consumer_warps, int silu) {
-    extern __shared__ __align__(128) uint8_t smem_ga[];
-    const uint32_t row_bytes = (uint32_t)C * 2u;
-    const int tile_rows = kGnKU * RL;
-    const uint32_t tile_bytes = (uint32_t)tile_rows * row_bytes;
-    const uint32_t ring = smem_u32(smem_ga);
-    const uint32_t bar_full = ring + kRing * tile_bytes, bar_empty = bar_full + 8 * kRing;
-    const int chunk = blockIdx.x, n = blockIdx.y;
-    const long long r0 = (long long)chunk * rows_per_chunk;
-    long long nrows = rows_per_sample - r0;
-    if (nrows > rows_per_chunk) nrows = rows_per_chunk;
-    if (nrows <= 0) return;
-    ring_init(bar_full, bar_empty, consumer_warps);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long long row_base = (long long)n * rows_per_sample + r0;
-    if (warp == consumer_warps) {
-        ring_produce(reinterpret_cast<const uint8_t*>(x + row_base * C), nrows, tile_rows, row_bytes, ring, tile_bytes, bar_full, bar_empty);
-        return;
-    }
-    const bool active = (int)threadIdx.x < vpr * RL;
-    const int v = threadIdx.x % vpr, rl = threadIdx.x / vpr;
-    const int cg = C / G;
-    float sc[8], sh[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-        const int c = v * 8 + e;
-        const int g = c / cg;
-        const float mean = stats[(n * G + g) * 2], rstd = stats[(n * G + g) * 2 + 1];
-        sc[e] = rstd * gamma[c];
-        sh[e] = beta[c] - mean * sc[e];
-    }
-    int st = 0;
-    uint32_t ph = 0;
-    for (long long r = 0; r < nrows; r += tile_rows) {
-        const long long left = nrows - r;
-        const int rows = left < tile_rows ? (int)left : tile_rows;
-        mbar_wait(bar_full + 8 * st, ph);
-        const uint8_t* tile = smem_ga + (size_t)st * tile_bytes;
-        uint4 u[kGnKU];
-#pragma unroll
-        for (int k = 0; k < kGnKU; ++k) {
-            const int lr = k * RL + rl;
-            u[k] = (active && lr < rows) ? *reinterpret_cast<const uint4*>(tile + (size_t)lr * row_bytes + v * 16) : make_uint4(0, 0, 0, 0);
-        }
-#pragma unroll
-        for (int k = 0; k < kGnKU; ++k) {
-            const int lr = k * RL + rl;
-            if (active && lr < rows) *reinterpret_cast<uint4*>(y + (row_base + r + lr) * C + v * 8) = gn_apply8(u[k], sc, sh, silu);
-        }
-        __syncwarp();                                                  // loads consumed -> the stage may be overwritten
-        if (lane == 0) mbar_arrive(bar_empty + 8 * st);
-        if (++st == kRing) { st = 0; ph ^= 1; }
-    }
-}
-
 }  // namespace wiw
 
 using namespace wiw;
@@ -691,44 +377,7 @@ extern "C" int wiw_groupnorm(const void* x, void* y, int samples, long long rows
     WIW_REQUIRE(threads <= 1024, "C too large");
     float* partial = workspace;
     float* stats = workspace + (size_t)samples * kGnMaxChunks * G * 2;
-    static const int norm_v = getenv("WIW_NORM_V") ? atoi(getenv("WIW_NORM_V")) : 1;          // 2 = TMA-ring streaming variants (A/B: no faster)
     const double count = (double)rows_per_sample * (C / G);
-    if (norm_v >= 2 && vpr <= 256) {
-        // streaming kernels: (chunk, sample) CTAs of contiguous rows, ~2-3 CTAs per SM, 4-stage TMA ring each
-        const int tile_rows = kGnKU * RL;
-        const int cw = (threads + 31) / 32;
-        const size_t ring_bytes = (size_t)kRing * tile_rows * C * 2 + 128;
-        const size_t smem_stats = ring_bytes + (size_t)(2 * RL + 2) * C * sizeof(float);
-        static bool attr_set = false;
-        if (!attr_set) {
-            WIW_CHECK_CUDA(cudaFuncSetAttribute(gn_stats_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-            WIW_CHECK_CUDA(cudaFuncSetAttribute(gn_apply_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-            attr_set = true;
-        }
-        WIW_REQUIRE(smem_stats <= 160 * 1024, "GroupNorm tile does not fit shared memory");
-        auto pick = [&](int target_ctas) {
-            long long chunks = (target_ctas + samples - 1) / samples;
-            if (chunks > kGnMaxChunks) chunks = kGnMaxChunks;
-            if (chunks < 1) chunks = 1;
-            long long rpc = (rows_per_sample + chunks - 1) / chunks;
-            rpc = (rpc + tile_rows - 1) / tile_rows * tile_rows;              // whole tiles per CTA
-            return rpc;
-        };
-        const long long rpc = pick(2 * num_sms());
-        const int chunks = (int)((rows_per_sample + rpc - 1) / rpc);
-        gn_stats_stream_kernel<<<dim3(chunks, samples), (cw + 1) * 32, smem_stats, stream>>>(
-            static_cast<const __half*>(x), partial, rows_per_sample, C, G, rpc, vpr, RL, cw);
-        WIW_CHECK_CUDA(cudaGetLastError());
-        const int warps = samples * G;
-        gn_finalize_kernel<<<(warps * 32 + 255) / 256, 256, 0, stream>>>(partial, stats, samples, G, chunks, count, eps);
-        WIW_CHECK_CUDA(cudaGetLastError());
-        const long long arpc = pick(2 * num_sms());
-        const int achunks = (int)((rows_per_sample + arpc - 1) / arpc);
-        gn_apply_stream_kernel<<<dim3(achunks, samples), (cw + 1) * 32, ring_bytes, stream>>>(
-            static_cast<const __half*>(x), static_cast<__half*>(y), stats, gamma, beta, rows_per_sample, C, G, arpc, vpr, RL, cw, silu);
-        WIW_CHECK_CUDA(cudaGetLastError());
-        return 0;
-    }
     // Whole waves of resident CTAs: 43 chunks x 28 frames = 1204 CTAs on 592 resident slots is 2.03 waves -- the 0.03 costs a
     // full CTA time.  Round the chunk count DOWN so samples * chunks <= waves * occupancy * SMs.
     static const int wavefit = getenv("WIW_WAVEFIT") ? atoi(getenv("WIW_WAVEFIT")) : 1;       // development aid for A/B runs
@@ -774,7 +423,7 @@ extern "C" int wiw_layernorm(const void* x, void* y, long long M, int C, const f
     const __half* xi = static_cast<const __half*>(x);
     __half* yo = static_cast<__half*>(y);
     const int nvec = C / 8;
-    static const int norm_v = getenv("WIW_NORM_V") ? atoi(getenv("WIW_NORM_V")) : 3;          // 3 = lane-group kernel (default), 1 = one warp per row, 2 = TMA-ring streaming
+    static const int norm_v = getenv("WIW_NORM_V") ? atoi(getenv("WIW_NORM_V")) : 3;          // 3 = lane-group kernel (default), 1 = one warp per row (development aid for A/B runs)
     static const int wavefit = getenv("WIW_WAVEFIT") ? atoi(getenv("WIW_WAVEFIT")) : 1;       // development aid for A/B runs
     if (norm_v == 3) {
         auto launch = [&](auto kern, int lpr) -> int {
@@ -806,33 +455,6 @@ extern "C" int wiw_layernorm(const void* x, void* y, long long M, int C, const f
         if (nvec <= 96) return launch(layernorm_lpr_kernel<32, 3>, 32);
         if (nvec <= 128) return launch(layernorm_lpr_kernel<32, 4>, 32);
         // C > 1024: fall through to the one-warp-per-row kernel (A/B on B200: C = 320 +52 %, 640 +11 %, 960 +34 %, 1280 -10 %)
-    }
-    if (norm_v == 2) {
-        static bool attr_set = false;
-        if (!attr_set) {            // (all instantiations share one function-pointer type: set each explicitly)
-            WIW_CHECK_CUDA(cudaFuncSetAttribute(layernorm_stream_kernel<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-            WIW_CHECK_CUDA(cudaFuncSetAttribute(layernorm_stream_kernel<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-            WIW_CHECK_CUDA(cudaFuncSetAttribute(layernorm_stream_kernel<3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-            WIW_CHECK_CUDA(cudaFuncSetAttribute(layernorm_stream_kernel<5, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-            WIW_CHECK_CUDA(cudaFuncSetAttribute(layernorm_stream_kernel<8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-            attr_set = true;
-        }
-        auto launch = [&](auto kern, int rpw) -> int {
-            const int tile_rows = 8 * rpw;
-            const size_t smem = (size_t)kRing * tile_rows * C * 2 + 128;
-            WIW_REQUIRE(smem <= 160 * 1024, "LayerNorm tile does not fit shared memory");
-            long long rows_per_cta = (M + 2 * num_sms() - 1) / (2 * num_sms());
-            rows_per_cta = (rows_per_cta + tile_rows - 1) / tile_rows * tile_rows;
-            const unsigned grid = (unsigned)((M + rows_per_cta - 1) / rows_per_cta);
-            kern<<<grid, 288, smem, stream>>>(xi, yo, gamma, beta, tab, tab_div, tab_mod, M, C, eps, rows_per_cta);
-            WIW_CHECK_CUDA(cudaGetLastError());
-            return 0;
-        };
-        if (nvec <= 32) return launch(layernorm_stream_kernel<1, 4>, 4);
-        if (nvec <= 64) return launch(layernorm_stream_kernel<2, 4>, 4);
-        if (nvec <= 96) return launch(layernorm_stream_kernel<3, 2>, 2);
-        if (nvec <= 160) return launch(layernorm_stream_kernel<5, 1>, 1);
-        return launch(layernorm_stream_kernel<8, 1>, 1);
     }
     const int wpb = 8;                                    // warps per block
     auto grid = [&](int R) { return (unsigned)((M + (long long)wpb * R - 1) / ((long long)wpb * R)); };
