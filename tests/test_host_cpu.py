@@ -85,3 +85,38 @@ def test_latent_noise_matches_oracle():
     assert torch.equal(sample_latent_noise_(noise.clone(), acts), ref)
     with pytest.raises(AssertionError):
         sample_latent_noise_(torch.zeros(2, 4, 2, 8), torch.tensor([4, 2]))
+
+
+def test_tile_shape_pickers():
+    """Host-side M-tile / N-tile selection (ops._box3, _tbox, pick_bn): every pick is a legal tile (product 128, power-of-two
+    extents the per-warp TMA store boxes can split) and fills the north-star feature maps as DESIGN.md section 4 states."""
+    from wiw_b200 import ops
+
+    def util3(w, h, n, box):
+        bx, by, bz = box
+        return (min(w, bx) / bx if w < bx else w / (-(-w // bx) * bx)) * (h / (-(-h // by) * by)) * (n / (-(-n // bz) * bz))
+
+    for (w, h, n) in [(128, 72, 28), (64, 36, 28), (32, 18, 28), (16, 9, 28), (16, 8, 16), (8, 4, 16), (2, 1, 16), (1024, 576, 14), (16, 9, 3)]:
+        bx, by, bz = ops._box3(w, h, n)
+        assert bx * by * bz == 128 and all(v & (v - 1) == 0 for v in (bx, by, bz))
+    assert ops._box3(128, 72, 28) == (128, 1, 1) and ops._box3(32, 18, 28) == (32, 2, 2) and ops._box3(16, 9, 28) == (16, 2, 4)
+    assert util3(16, 9, 28, ops._box3(16, 9, 28)) == pytest.approx(0.9) and util3(16, 9, 28, (16, 8, 1)) == pytest.approx(0.5625)
+    for (s, f) in [(9216, 14), (2304, 14), (576, 14), (144, 14), (128, 8), (2, 8)]:
+        bx, by = ops._tbox(s, f)
+        assert bx * by == 128
+    assert ops._tbox(144, 14) == (16, 8) and ops._tbox(576, 14) == (64, 2) and ops._tbox(9216, 14) == (128, 1)
+    # N-tiles: fewest tiles, then narrowest; GEGLU tiles divide N
+    assert ops.pick_bn(320) == 160 and ops.pick_bn(640) == 224 and ops.pick_bn(960) == 256 and ops.pick_bn(1280) == 256
+    assert ops.pick_bn(2560, geglu=True) == 256 and ops.pick_bn(512, geglu=True) == 256 and ops.pick_bn(64) == 64
+    with pytest.raises(ValueError):
+        ops.pick_bn(100)
+
+
+def test_pair_layout_for_cfg_split():
+    from wiw_b200 import sharding
+    pairs, owner = sharding.pair_layout(3, 8)
+    assert pairs == 4 and owner == [(0, 0), (2, 0), (4, 0)]
+    assert sharding.pair_branch_indices(3, 0, 8) == [0] and sharding.pair_branch_indices(3, 1, 8) == [0]
+    assert sharding.pair_branch_indices(3, 5, 8) == [2] and sharding.pair_branch_indices(3, 7, 8) == []
+    pairs, owner = sharding.pair_layout(5, 4)
+    assert owner == [(0, 0), (2, 0), (0, 1), (2, 1), (0, 2)] and sharding.pair_branch_indices(5, 3, 4) == [1, 3]
