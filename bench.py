@@ -232,22 +232,36 @@ def main():
     for _ in range(args.warmup):
         step()
     barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
-    if sampler:
-        sampler.start()
-    L.COUNTERS["gpu_launches"] = 0
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    if args.profiler_range:
-        torch.cuda.profiler.start()
-    e0.record()
-    for _ in range(args.steps):
-        step()
-    e1.record()
-    barrier()
-    if args.profiler_range:
-        torch.cuda.profiler.stop()
+
+    def timed_region():
+        sampler = ClockSampler(local) if rank == 0 else None
+        if sampler:
+            sampler.start()
+        L.COUNTERS["gpu_launches"] = 0
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if args.profiler_range:
+            torch.cuda.profiler.start()
+        e0.record()
+        for _ in range(args.steps):
+            step()
+        e1.record()
+        barrier()
+        if args.profiler_range:
+            torch.cuda.profiler.stop()
+        return e0, e1, (sampler.stop() if sampler else None)
+
+    e0, e1, clocks = timed_region()
+    # a region that saw a hardware / thermal slowdown is not a measurement: re-measure once (sw_power_cap is normal on this pod)
+    bad = {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    redo = torch.tensor([1 if (clocks and bad & set(clocks.get("reasons", []))) else 0], device=dev)
+    if world > 1:
+        dist.broadcast(redo, src=0)
+    if int(redo.item()):
+        first = clocks
+        e0, e1, clocks = timed_region()
+        if clocks is not None:
+            clocks["remeasured_after"] = first.get("reasons") if first else None
     launches = L.COUNTERS["gpu_launches"]
-    clocks = sampler.stop() if sampler else None
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)

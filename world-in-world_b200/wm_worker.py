@@ -484,10 +484,10 @@ def main(argv: List[str]) -> None:
         import torch.distributed as dist
         if args.rank == 0:                                     # the process the manager spawned: start ranks 1..R-1
             args.master_port = args.master_port or _free_port()
-            base = [a for a in argv[:-1] if not a.startswith(("--rank", "--master_port", "--device"))]
-            for r in range(1, args.gpus):
-                helpers.append(subprocess.Popen([sys.executable, os.path.abspath(__file__)] + base +
-                                                [f"--rank={r}", f"--master_port={args.master_port}", "-1"], stdin=subprocess.DEVNULL))
+            for r in range(1, args.gpus):                     # same flags; argparse keeps the LAST occurrence of the overrides
+                helpers.append(subprocess.Popen([sys.executable, os.path.abspath(__file__)] + list(argv[:-1]) +
+                                                [f"--rank={r}", f"--master_port={args.master_port}", f"--device=cuda:{r}", "-1"],
+                                                stdin=subprocess.DEVNULL))
         args.device = f"cuda:{args.rank}"
         torch.cuda.set_device(args.rank)
         dist.init_process_group("cpu:gloo,cuda:nccl", init_method=f"tcp://127.0.0.1:{args.master_port}", rank=args.rank,
