@@ -6,8 +6,6 @@ executes the *documented meaning* of the descriptor (include/wiw.h) on host memo
 product -- and the result is compared with torch's own conv / linear.  What this pins on the CPU: the tap tables (zero
 padding, the space-to-depth view of the stride-2 conv, the frame taps of the temporal conv), weight layouts, bias / table /
 residual / aux / AlphaBlender semantics and the tile-shape choices staying inside the descriptor contract."""
-import ctypes
-
 import numpy as np
 import pytest
 import torch
@@ -18,82 +16,16 @@ from wiw_b200 import lib as L
 from wiw_b200 import ops
 
 
-def _arr(ptr, n, dtype):
-    if not ptr:
-        return None
-    buf = (ctypes.c_char * (n * np.dtype(dtype).itemsize)).from_address(ptr)
-    return np.frombuffer(buf, dtype=dtype)
+import os
+import sys
 
-
-class FakeLib:
-    """Executes a wiw_gemm_desc the way include/wiw.h documents it (fp32 accumulation, fp16 output)."""
-
-    def __init__(self):
-        self.calls = []
-
-    def wiw_conv_gemm(self, d, stream):
-        ad, ast = list(d.a_dim), list(d.a_stride)
-        od, ost = list(d.out_dim), list(d.out_stride)
-        taps, cpt = d.num_taps, d.chunks_per_tap
-        cin = cpt * 64
-        assert d.k_total == taps * cin and d.bx * d.by * max(d.bz, 1) == 128 and d.bn % 32 == 0 and 32 <= d.bn <= 256
-        a_span = 1 + sum((ad[i] - 1) * ast[i] for i in range(5))
-        A = _arr(d.a, a_span, np.float16).astype(np.float32)
-        Wm = _arr(d.w, d.n_total * d.k_total, np.float16).astype(np.float32).reshape(d.n_total, d.k_total)
-        n_out = d.n_total // 2 if d.geglu else d.n_total
-        assert od[0] == n_out
-        X, Y, N = od[1], od[2], od[3]
-        acc = np.zeros((N, Y, X, d.n_total), np.float32)
-        xs, ys, ns = np.arange(X), np.arange(Y), np.arange(N)
-        for t in range(taps):
-            cb, ox, p, oy = d.tap_cbase[t], d.tap_ox[t], d.tap_p[t], d.tap_oy[t]
-            xi, yi = xs + ox, ys + oy
-            ok = ((xi >= 0) & (xi < ad[1]))[None, None, :] & ((yi >= 0) & (yi < ad[3]))[None, :, None] & np.ones((N, 1, 1), bool)
-            base = (ns[:, None, None] * ast[4] + np.clip(yi, 0, ad[3] - 1)[None, :, None] * ast[3] + p * ast[2]
-                    + np.clip(xi, 0, ad[1] - 1)[None, None, :] * ast[1])
-            ch = cb + np.arange(cin)
-            chok = ch < ad[0]                                                  # channels past the tensor read as zero (TMA OOB fill)
-            patch = A[(base[..., None] + np.clip(ch, 0, ad[0] - 1) * ast[0])] * chok * ok[..., None]
-            acc += patch @ Wm[:, t * cin:(t + 1) * cin].T
-        if d.bias:
-            acc += _arr(d.bias, d.n_total, np.float32)
-        if d.tab:
-            grow = (ns[:, None, None] * Y + ys[None, :, None]) * X + xs[None, None, :]
-            rows = (grow // d.tab_div) % d.tab_mod
-            stride = d.tab_stride if d.tab_stride > 0 else d.n_total
-            tab = _arr(d.tab, (d.tab_mod - 1) * stride + d.n_total, np.float16).astype(np.float32)
-            acc += tab[rows[..., None] * stride + np.arange(d.n_total)]
-        if d.act == 1:
-            acc = acc / (1.0 + np.exp(-acc))
-        if d.geglu:
-            bn, hb = d.bn, d.bn // 2
-            v = acc.reshape(N, Y, X, d.n_total // bn, bn)
-            gate = torch.from_numpy(np.ascontiguousarray(v[..., hb:]))
-            acc = (v[..., :hb] * F.gelu(gate).numpy()).reshape(N, Y, X, n_out)
-        out = acc * d.s_acc
-        o_span = 1 + sum((od[i] - 1) * ost[i] for i in range(4))
-        idx = (ns[:, None, None, None] * ost[3] + ys[None, :, None, None] * ost[2] + xs[None, None, :, None] * ost[1]
-               + np.arange(n_out)[None, None, None, :] * ost[0])
-        if d.res:
-            out = out + d.s_res * _arr(d.res, o_span, np.float16).astype(np.float32)[idx]
-        if d.aux:
-            out = out + d.s_aux * _arr(d.aux, o_span, np.float16).astype(np.float32)[idx]
-        O = _arr(d.out, o_span, np.float16)
-        O[idx] = out.astype(np.float16)
-        self.calls.append((d.bx, d.by, d.bz, d.bn))
-        return 0
-
-    def wiw_last_error(self):
-        return b""
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "helpers"))
+import cabi_emulator  # noqa: E402
 
 
 @pytest.fixture()
 def fake(monkeypatch):
-    lib = FakeLib()
-    monkeypatch.setattr(L, "require_device", lambda: lib)
-    monkeypatch.setattr(L, "stream_ptr", lambda: None)
-    monkeypatch.setattr(ops, "_chk", lambda x: None)
-    return lib
+    return cabi_emulator.install(monkeypatch)
 
 
 def rnd(*shape, seed=0, scale=1.0):
