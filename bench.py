@@ -77,9 +77,9 @@ class ClockSampler:
 # ============================================================================= CPU reference arm
 def cpu_reference_sample(steps: int, warmup: int):
     """The reference's CPU implementation of the path = the oracle port (the vendored fork itself lives under
-    /root/reference, which does not exist on the GPU box).  Bounded sample: ONE UNet forward of the full
-    1.53 B-parameter architecture (CFG pair x 14 frames) at 8x16 latents instead of 72x128, fp32, all host
-    threads; frames/sec of the named workload is extrapolated by the algorithmic-FLOP ratio."""
+    /root/reference, which does not exist on the GPU box).  Bounded sample: UNet forwards of the full
+    1.53 B-parameter architecture (CFG pair x 14 frames) at 16x32 latents instead of 72x128, fp32, host threads
+    (10-15 s of CPU work with the warm-up); frames/sec of the named workload is extrapolated by the algorithmic-FLOP ratio."""
     from torch.utils.flop_counter import FlopCounterMode
     from oracle import svd_oracle as O
     import wiw_b200  # noqa: F401
@@ -102,7 +102,7 @@ def cpu_reference_sample(steps: int, warmup: int):
         leaf = name.rsplit(".", 1)[-1]
         sd[name] = t * (0.7 / fan ** 0.5) if (leaf == "weight" and len(shape) > 1) else (1 + 0.1 * t if leaf == "weight" else 0.05 * t)
     cfg = O.UNetCfg()
-    sh, sw = 8, 16
+    sh, sw = 16, 32                                    # ~3 s per forward on 16 host threads: warm-up + timed forwards = 10-15 s of CPU work
     x = torch.randn(2, F, 8, sh, sw, generator=g)
     enc = torch.randn(2, 1, 1024, generator=g)
     ids = torch.tensor([[6.0, 127.0, 0.02]] * 2)
