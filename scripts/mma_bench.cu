@@ -101,8 +101,18 @@ static int run(Cfg c, int grid) {
     return e ? 1 : 0;
 }
 
-int main() {
+int main(int argc, char** argv) {
     const int grid = 148;
+    if (argc > 1 && !strcmp(argv[1], "swap")) {
+        // cost of the M extent (the swap-AB question: weights as the M operand, 256 pixels as N): M = 64 / 128 per instruction
+        for (int n : {64, 128, 256}) {
+            if (run({128, n, 0, 1, 4, 2, 1, 0}, grid)) return 1;      // cta_group::2, M = 128 (64 rows per CTA)
+            if (run({256, n, 0, 1, 4, 2, 1, 0}, grid)) return 1;      // cta_group::2, M = 256 (reference point)
+            if (run({64, n, 0, 1, 4, 1, 1, 0}, grid)) return 1;       // cta_group::1, M = 64
+            if (run({128, n, 0, 1, 4, 1, 1, 0}, grid)) return 1;      // cta_group::1, M = 128 (reference point)
+        }
+        return 0;
+    }
     for (int single : {1, 0}) {
         for (int n : {32, 64, 80, 128, 160, 192, 224, 256})
             if (run({128, n, 0, 1, 4, 1, 1, single}, grid)) return 1;
