@@ -71,3 +71,19 @@ def test_rollout_and_decode_sequencing_vs_reference_pipeline(emu, golden_dir):
     frames = (f32 / 2 + 0.5).clamp(0, 1).numpy()
     assert O.psnr(frames, g["frames"][0]) >= 45.0
     assert O.psnr(u8.numpy().astype(np.float32) / 255.0, g["frames"][0]) >= 45.0
+
+
+def test_vae_encoder_sequencing_vs_golden(emu, golden_dir):
+    """the SD-VAE encoder + quant_conv on the implicit-GEMM / GroupNorm wrappers reproduces the
+    reference's fp32 posterior mean (frontend_tiny.npz) -- asymmetric stride-2 taps, shortcut convs, single-head attention and
+    the quant_conv fold."""
+    from wiw_b200.engine import VAEEncoderEngine
+    from wiw_b200.frontend import vae_encoder_param_spec
+    g = np.load(os.path.join(golden_dir, "frontend_tiny.npz"))
+    c = TINY_VAE
+    esd = W.random_init(vae_encoder_param_spec(c.block_out_channels, c.layers_per_block, c.latent_channels), 13)
+    enc = VAEEncoderEngine(c, esd, "cpu")
+    got = enc.encode_mode(torch.from_numpy(g["image"])).float()
+    ref = torch.from_numpy(g["latent_mode"])
+    assert got.shape == ref.shape
+    assert rel_rms(got, ref) < 1e-2, rel_rms(got, ref)
