@@ -119,3 +119,29 @@ def test_worker_request_path_on_host(emu, tmp_path):
     full = nav.inference(WW.action_ids_idx_encode(req["b_action"]), req["b_image"])          # uint8 [1, 8, 3, 64, 128]
     ref = (np.clip(WW.images_to_tensor(full, save_size=(48, 40)).numpy(), 0, 1) * 255).astype(np.uint8)
     assert np.array_equal(pf, ref)
+
+
+def test_files_mode_writes_reference_bytes(emu, tmp_path):
+    """Files mode (<save_dir>/<idx>.jpg + action_seq.json): the JPEGs written from the device-side resize equal the ones the
+    reference's images_to_tensor -> save_predict chain writes from the same full-resolution frames."""
+    from wiw_b200 import wm_worker as WW
+
+    class Nav:                                             # fixed full-resolution frames: isolates the output stage
+        device = torch.device("cpu")
+
+        def inference(self, actions, images_u8, ow=None, oh=None, on_device=False, **kw):
+            g = torch.Generator().manual_seed(5)
+            return torch.randint(0, 256, (actions.shape[0], 8, 3, 64, 128), generator=g, dtype=torch.uint8)
+
+    args = WW.build_parser().parse_args(["--width", "128", "--height", "64", "--out_width", "48", "--out_height", "40", "--num_frames", "8"])
+    worker = WW.WorldModelWorker(args, Nav())
+    acts = np.array([[4, 1, 2, 2, 1, 3, 1, 1]], dtype=np.int64)
+    req = {"b_action": acts, "b_image": np.zeros((1, 3, 64, 128), np.uint8), "save_dirs": [str(tmp_path / "new")], "request_model_name": "igen"}
+    out = worker.do_some_tasks(req)
+    assert out == {"save_dirs": req["save_dirs"]}
+    full = Nav().inference(torch.zeros(1, 8, 8), None).numpy()
+    WW.save_predict(WW.images_to_tensor(full, save_size=(48, 40)).numpy(), acts, [str(tmp_path / "ref")])
+    names = sorted(os.listdir(tmp_path / "ref"))
+    assert names == sorted(os.listdir(tmp_path / "new")) and len(names) == 9
+    for n in names:
+        assert open(tmp_path / "ref" / n, "rb").read() == open(tmp_path / "new" / n, "rb").read(), n

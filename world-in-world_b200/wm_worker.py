@@ -286,8 +286,9 @@ class WorldModelWorker:
             if return_objects:
                 # only the 480x480 uint8 result crosses PCIe
                 return {"pred_frames": self.resized_frames(frames).cpu().numpy(), "save_dirs": save_dirs}
-            video = images_to_tensor(frames.cpu().numpy(), save_size=(self.args.out_width, self.args.out_height)).numpy()
-            save_predict(video, b_action, save_dirs)
+            # files mode (saver.py:221-274): same device-side resize + requantisation, the JPEGs hold exactly the bytes the reference's
+            # images_to_tensor -> save_predict chain would write
+            save_predict_u8(self.resized_frames(frames).cpu().numpy(), b_action, save_dirs)
             return {"save_dirs": save_dirs}
         except Exception:                       # never die inside task_fn (SURVEY.md 8b "Errors")
             traceback.print_exc()
