@@ -42,6 +42,27 @@ def peaks():
     return 1590.0, 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic() -> dict:
+    """roofline.traffic = dram__bytes_read.sum + dram__bytes_write.sum of ONE representative launch of the dominant kernel, from
+    the JSON that scripts/ncu_traffic.py extracts from the latest committed `ncu --set full` capture.  The JSON records the
+    sha256 of the kernel source it was captured from: a capture older than the current wiw_gemm.cu yields traffic = null."""
+    import glob
+    import hashlib
+    cands = sorted(glob.glob(os.path.join(REPO, "profiles", "r*_ncu_traffic.json")))
+    if not cands:
+        return {"traffic": None, "traffic_launch": "no ncu capture committed (profiles/r*_ncu_traffic.json)"}
+    d = json.load(open(cands[-1]))
+    src = os.path.join(REPO, "world-in-world_b200", "csrc", "wiw_gemm.cu")
+    sha = hashlib.sha256(open(src, "rb").read()).hexdigest()[:16]
+    if d.get("kernel_source_sha16") != sha:
+        return {"traffic": None, "traffic_launch": f"{os.path.basename(cands[-1])} was captured from an older wiw_gemm.cu "
+                                                   f"({d.get('kernel_source_sha16')} != {sha}): stale, not reported"}
+    k = d["dominant"]
+    return {"traffic": k["dram_bytes"], "traffic_launch": f"{k['launch']}: {k['dram_read_bytes'] / 1e6:.1f} MB read + "
+            f"{k['dram_write_bytes'] / 1e6:.1f} MB written per launch, algorithmic {k['algorithmic_bytes'] / 1e6:.1f} MB "
+            f"({os.path.basename(cands[-1])})"}
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -75,25 +96,21 @@ class ClockSampler:
 
 
 # ============================================================================= CPU reference arm
-def cpu_reference_sample(steps: int, warmup: int):
+def cpu_reference_sample(steps: int, warmup: int, max_forwards: int = 8):
     """The reference's CPU implementation of the path = the oracle port (the vendored fork itself lives under
     /root/reference, which does not exist on the GPU box).  Bounded sample: UNet forwards of the full
-    1.53 B-parameter architecture (CFG pair x 14 frames) at 16x32 latents instead of 72x128, fp32, host threads
-    (10-15 s of CPU work with the warm-up); frames/sec of the named workload is extrapolated by the algorithmic-FLOP ratio."""
+    1.53 B-parameter architecture (CFG pair x 14 frames) at 36x64 latents (a quarter of 72x128 in each... half per axis),
+    fp32, on the host threads a short sweep finds fastest; frames/sec of the named workload is extrapolated by the
+    algorithmic-FLOP ratio.  `steps` forwards are requested; at most `max_forwards` are timed so that the run stays bounded."""
     from torch.utils.flop_counter import FlopCounterMode
     from oracle import svd_oracle as O
     import wiw_b200  # noqa: F401
     from wiw_b200 import weights as Wt
     from wiw_b200.config import FULL_UNET
-    # 128 intra-op threads on these small-latent tensors ran 40x SLOWER than 8 (measured on the GPU box:
-    # 135 s vs 3 s per forward -- oversubscription), so the baseline uses the thread count that is fastest
-    # for it: min(16, schedulable cores).
     try:
         avail = len(os.sched_getaffinity(0))
     except AttributeError:
         avail = os.cpu_count() or 1
-    torch.set_num_threads(max(1, min(16, avail)))
-    cores = torch.get_num_threads()
     g = torch.Generator().manual_seed(0)
     sd = {}
     for name, shape in Wt.unet_param_spec(FULL_UNET):
@@ -102,36 +119,54 @@ def cpu_reference_sample(steps: int, warmup: int):
         leaf = name.rsplit(".", 1)[-1]
         sd[name] = t * (0.7 / fan ** 0.5) if (leaf == "weight" and len(shape) > 1) else (1 + 0.1 * t if leaf == "weight" else 0.05 * t)
     cfg = O.UNetCfg()
-    sh, sw = 16, 32                                    # ~3 s per forward on 16 host threads: warm-up + timed forwards = 10-15 s of CPU work
-    x = torch.randn(2, F, 8, sh, sw, generator=g)
     enc = torch.randn(2, 1, 1024, generator=g)
     ids = torch.tensor([[6.0, 127.0, 0.02]] * 2)
     aids = O.action_ids_idx_encode(torch.tensor([[4] + [1] * (F - 1)])).float()
+
+    def fwd(x):
+        t0 = time.perf_counter()
+        O.unet_forward(sd, cfg, x, torch.tensor(1.0), enc, ids, aids)
+        return time.perf_counter() - t0
+
     with torch.no_grad():
+        # thread sweep on a small forward (16x32 latents, ~3 s each): 128 intra-op threads ran 40x SLOWER than 8 on the GPU box
+        # in round 1 (oversubscription on small tensors), so the count is measured, not assumed
+        xs = torch.randn(2, F, 8, 16, 32, generator=g)
+        sweep = {}
+        for n in sorted({c for c in (8, 16, 32, 64, 128) if c <= avail} | {min(avail, 8)}):
+            torch.set_num_threads(n)
+            if not sweep:
+                fwd(xs)                                                         # first-touch warm-up
+            sweep[n] = fwd(xs)
+            if len(sweep) > 1 and sweep[n] > 1.5 * min(sweep.values()):
+                break                                                           # already on the wrong side of the optimum
+        cores = min(sweep, key=sweep.get)
+        torch.set_num_threads(cores)
+        sh, sw = 36, 64
+        x = torch.randn(2, F, 8, sh, sw, generator=g)
         with FlopCounterMode(display=False) as fc:
-            O.unet_forward(sd, cfg, x, torch.tensor(1.0), enc, ids, aids)
+            w0 = fwd(x)                                                         # counted pass doubles as the warm-up at this size
         sample_tflop = fc.get_total_flops() / 1e12
-        for _ in range(warmup):
-            O.unet_forward(sd, cfg, x, torch.tensor(1.0), enc, ids, aids)
-        ts = []
-        for _ in range(steps):
-            t0 = time.perf_counter()
-            O.unet_forward(sd, cfg, x, torch.tensor(1.0), enc, ids, aids)
-            ts.append(time.perf_counter() - t0)
+        for _ in range(max(0, min(warmup, 1) - 1)):
+            fwd(x)
+        n_timed = max(1, min(steps, max_forwards))
+        ts = [fwd(x) for _ in range(n_timed)]
     sec = float(np.mean(ts))
     rate = sample_tflop / sec                                        # CPU TFLOP/s on this graph
     clip_tflop = 25 * TFLOP_UNET_FWD + TFLOP_VAE_DEC
     fps = F / (clip_tflop / rate)
     return {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
-            "sample": f"1 UNet forward, full 1.53B-param arch, CFG pair x {F} frames at {sh}x{sw} latents "
-                      f"({sample_tflop:.3f} TFLOP, {sec:.2f} s => {rate:.3f} TFLOP/s fp32); frames/s extrapolated over the "
+            "thread_sweep_s_per_small_forward": {str(k): round(v, 2) for k, v in sweep.items()},
+            "sample": f"{n_timed} UNet forward(s) (of {steps} steps requested; bounded), full 1.53B-param arch, CFG pair x {F} frames at "
+                      f"{sh}x{sw} latents ({sample_tflop:.3f} TFLOP, {sec:.2f} s each => {rate:.3f} TFLOP/s fp32 on {cores} threads, "
+                      f"fastest of a thread sweep over {sorted(sweep)} of {avail} schedulable cores); frames/s extrapolated over the "
                       f"{clip_tflop:.0f} TFLOP of one 25-step 576x1024 clip"}, sec
 
 
 def run_reference(args, rank: int, world: int):
     if rank != 0:
         return
-    cb, sec = cpu_reference_sample(max(1, args.steps), min(args.warmup, 1))
+    cb, sec = cpu_reference_sample(max(1, args.steps), min(args.warmup, 1), max_forwards=6)
     line = {"metric": METRIC, "value": cb["value"], "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "impl": "reference", "config": workload_config(world), "cpu_baseline": cb,
@@ -182,7 +217,8 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        # data plane NCCL (frame all-gathers over NVLink), control plane gloo (the sharded worker broadcasts the request payload)
+        dist.init_process_group("cpu:gloo,cuda:nccl", device_id=dev)
     N_STEPS = 25
     usd = Wt.random_init_on_device(Wt.unet_param_spec(FULL_UNET), 0, dev)
     vsd = Wt.random_init_on_device(Wt.vae_decoder_param_spec(FULL_VAE), 1, dev)
@@ -306,10 +342,7 @@ def main():
                 "achieved": round(ach, 1), "peak": peak, "unit": "TFLOP/s", "frac": round(ach / peak, 4), "peak_source": how,
                 "launches_per_unet_forward": len(prof), "algorithmic_tflop_per_unet_forward": round(g_flop / 1e12, 3),
                 "kernel_ms_per_unet_forward": round(g_ms, 3), "share_of_unet_forward": round(g_ms / unet_ms, 3),
-                # dram__bytes_read.sum + dram__bytes_write.sum of ONE representative launch from the committed `ncu --set full`
-                # capture (profiles/r01_ncu_full_v5.md): conv3x3 28x72x128 320->320, algorithmic bytes 332.1e6 (traffic / algorithmic = 0.91)
-                "traffic": 300.9e6, "traffic_launch": "conv3x3 28x72x128 320->320 (K=2880, N=320): 167.1 MB read + 133.8 MB written, "
-                                                      "algorithmic 332.1 MB; per-shape table in profiles/r01_ncu_full_v5.md"}
+                **ncu_traffic()}
         stages = {"unet_forward_ms": round(unet_ms, 2), "vae_decode_ms": round(dec_ms, 2),
                   "unet_forward_tflops": round((TFLOP_UNET_FWD - TFLOP_UNET_REMOVABLE) / unet_ms * 1e3, 1),
                   "unet_forward_frac_of_peak": round((TFLOP_UNET_FWD - TFLOP_UNET_REMOVABLE) / unet_ms * 1e3 / peak, 4),
@@ -326,30 +359,70 @@ def main():
         clip = CLIPVisionModelWithProjection(CLIPVisionConfig(hidden_size=1280, intermediate_size=5120, num_hidden_layers=32,
                                                               num_attention_heads=16, patch_size=14, projection_dim=1024)).to(dev, torch.float16).eval()
         esd = {k: v.float() for k, v in Wt.random_init_on_device(vae_encoder_param_spec(), 2, dev).items()}
-        worker = wm_worker.WorldModelWorker(wargs, wm_worker.Navigator(wargs, ro, clip, esd, dev))
-        rng = np.random.default_rng(7 + rank)
-        b_image = torch.from_numpy(rng.integers(0, 256, size=(1, 3, H, W), dtype=np.uint8)).pin_memory().numpy()
-        req = {"b_action": acts.astype(np.int64), "b_image": b_image, "save_dirs": [f"/tmp/wiw_bench_{rank}"],
-               "request_model_name": "igen", "return_objects": [True]}
-        out = worker.do_some_tasks(req)                               # warm-up (also primes CLIP / cuDNN autotune)
-        assert out["pred_frames"].shape == (1, F, 3, 480, 480) and out["pred_frames"].dtype == np.uint8
+        nav = wm_worker.Navigator(wargs, ro, clip, esd, dev)
+        rng = np.random.default_rng(7)
+        if world == 1:
+            worker = wm_worker.WorldModelWorker(wargs, nav)
+            n_req = 1
+            serve = worker.do_some_tasks
+            api = "wm_worker.WorldModelWorker.do_some_tasks (request dict -> pred_frames uint8)"
+        else:
+            # BASELINE configs[2]: ONE request of `world` planner branches served by the R-GPU worker -- rank 0 owns the host buffers,
+            # broadcasts the payload (gloo), every rank rolls out its branch, one NCCL all-gather returns the resized uint8 frames
+            wargs.gpus, wargs.rank = world, rank
+            worker = wm_worker.ShardedWorldModelWorker(wargs, nav, rank, world)
+            n_req = world
+            serve = lambda r: worker.serve_request(r if rank == 0 else None)
+            api = (f"wm_worker.ShardedWorldModelWorker.serve_request: one {world}-branch request on rank 0 -> gloo broadcast -> "
+                   f"branch-sharded rollouts -> one NCCL all-gather of uint8 frames -> pred_frames on rank 0")
+        b_image = torch.from_numpy(rng.integers(0, 256, size=(n_req, 3, H, W), dtype=np.uint8)).pin_memory().numpy()
+        b_action = np.concatenate([np.random.default_rng(3 + r).integers(1, 4, size=(1, F)) for r in range(n_req)]).astype(np.int64)
+        b_action[:, 0] = 4
+        req = {"b_action": b_action, "b_image": b_image, "save_dirs": [f"/tmp/wiw_bench_{i}" for i in range(n_req)],
+               "request_model_name": "igen", "return_objects": [True] * n_req}
+        out = serve(req)                                              # warm-up (also primes CLIP / cuDNN autotune)
+        if rank == 0:
+            assert out["pred_frames"].shape == (n_req, F, 3, 480, 480) and out["pred_frames"].dtype == np.uint8 and "errors" not in out
         barrier()
         t0 = time.perf_counter()
         reps = max(1, min(args.steps, 2))
         for _ in range(reps):
-            out = worker.do_some_tasks(req)
+            out = serve(req)
         torch.cuda.synchronize()
         dt = torch.tensor([time.perf_counter() - t0], device=dev)
         if world > 1:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        e2e = {"value": world * F * reps / float(dt.item()), "unit": "frames/s", "h2d_bytes_per_step": int(b_image.nbytes + acts.nbytes),
-               "d2h_bytes_per_step": int(out["pred_frames"].nbytes), "api": "wm_worker.WorldModelWorker.do_some_tasks (request dict -> pred_frames uint8)",
-               "includes": "H2D of the uint8 observation, CLIP ViT-H + fp32 VAE encode (PyTorch), 25-step rollout, decode, "
+        e2e = {"value": n_req * F * reps / float(dt.item()), "unit": "frames/s", "h2d_bytes_per_step": int(b_image.nbytes + b_action.nbytes),
+               "d2h_bytes_per_step": int(n_req * F * 3 * 480 * 480), "api": api,
+               "includes": "H2D of the uint8 observation(s), CLIP ViT-H + fp32 VAE encode (PyTorch), 25-step rollout, decode, "
                            "Pillow-exact bicubic 480x480 + requantisation on the GPU, D2H of the uint8 frames"}
+
+    # ---- latency mode for fewer branches than GPUs: ONE branch on the pair (rank 0, rank 1), one CFG row each
+    cfg_split_ms = None
+    if world >= 2 and not args.cfg_split and not args.no_e2e:
+        grp01 = None
+        for k in range(world // 2):                       # collective: every rank creates every pair group
+            gk = dist.new_group([2 * k, 2 * k + 1])
+            grp01 = gk if k == 0 else grp01
+        if rank < 2:
+            gp = torch.Generator(device=dev).manual_seed(100)
+            lat_p = torch.randn(F, 4, h, w, generator=gp, device=dev, dtype=torch.float16) * sched.init_noise_sigma
+            il_p = torch.randn(4, h, w, generator=gp, device=dev, dtype=torch.float16)
+            ie_p = torch.randn(1, 1024, generator=gp, device=dev, dtype=torch.float16)
+            aids_p = wm_worker.action_ids_idx_encode(np.array([[4] + [1, 2, 3] * 4 + [1]]))[0].float()
+            for it in range(2):                           # first pass captures the nb = 1 CUDA graph
+                torch.cuda.synchronize()
+                ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                ea.record()
+                ro.decode(ro.denoise(lat_p, il_p, ie_p, aids_p, num_steps=N_STEPS, cfg_split_group=grp01))
+                eb.record()
+                torch.cuda.synchronize()
+            cfg_split_ms = ea.elapsed_time(eb)
+        barrier()
 
     cpu_b = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu_b, _ = cpu_reference_sample(1, 1)
+        cpu_b, _ = cpu_reference_sample(1, 1, max_forwards=1)
 
     if rank == 0:
         line = {"metric": METRIC, "value": round(value, 4), "unit": "frames/s", "n_gpus": world, "steps": args.steps,
@@ -359,6 +432,8 @@ def main():
                             "parallelism": f"cfg-split: {branches} branch(es), 2 GPUs per branch (one CFG row each), all-gather of v per Euler step"}
                            if args.cfg_split else workload_config(world)), "clocks": clocks,
                 "e2e": e2e, "gpu_launches": launches, "roofline": roof, "stages": stages, "cpu_baseline": cpu_b}
+        if cfg_split_ms is not None:
+            line["cfg_split_one_branch_ms"] = round(cfg_split_ms, 1)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -25,6 +25,34 @@ x = torch.randn(8192, 8192, device=DEV).half(); w = torch.randn(8192, 8192, devi
 ref = timeit(lambda: torch.matmul(x, w.t()))
 print(f"cublas 8192^3: {ref:.4f} ms ({2*8192**3/ref/1e9:.0f} TFLOP/s)", flush=True)
 del x, w
+
+
+def sdpa_rows():
+    """The library bar on the same box: F.scaled_dot_product_attention (what the reference calls, attention_processor.py:2383)
+    at the level-0 north-star shape, cuDNN and flash backends, plus flash_attn / flashinfer when they run on sm_100."""
+    import torch.nn.functional as Fn
+    from torch.nn.attention import SDPBackend, sdpa_kernel
+    imgs, heads, s, d = 28, 5, 9216, 64
+    q, k, v = (torch.randn(imgs, heads, s, d, device=DEV).half() for _ in range(3))
+    fl = 4.0 * imgs * heads * s * s * d
+    for name, be in (("cudnn", SDPBackend.CUDNN_ATTENTION), ("flash", SDPBackend.FLASH_ATTENTION), ("efficient", SDPBackend.EFFICIENT_ATTENTION)):
+        try:
+            with sdpa_kernel(be):
+                ms = timeit(lambda: Fn.scaled_dot_product_attention(q, k, v))
+            print(f"torch SDPA [{name}] imgs={imgs} heads={heads} S={s} d={d}: {ms:.4f} ms  {fl/ms/1e9:.0f} TFLOP/s", flush=True)
+        except Exception as e:
+            print(f"torch SDPA [{name}]: unavailable ({str(e).splitlines()[0][:120]})", flush=True)
+    try:
+        from flash_attn import flash_attn_func
+        qf, kf, vf = (t.transpose(1, 2).contiguous() for t in (q, k, v))
+        ms = timeit(lambda: flash_attn_func(qf, kf, vf))
+        print(f"flash_attn {__import__('flash_attn').__version__} same shape: {ms:.4f} ms  {fl/ms/1e9:.0f} TFLOP/s", flush=True)
+    except Exception as e:
+        print(f"flash_attn: unavailable ({str(e).splitlines()[0][:120]})", flush=True)
+
+
+if "sdpa" in sys.argv or "attn" in sys.argv:
+    sdpa_rows()
 NORM_ONLY = "norm" in sys.argv
 ATTN_ONLY = "attn" in sys.argv
 for (imgs, s, c) in [(28, 9216, 320), (28, 2304, 640), (28, 576, 1280), (28, 144, 1280), (28, 9216, 960)]:

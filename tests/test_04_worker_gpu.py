@@ -60,14 +60,25 @@ def test_worker_process_protocol(tmp_path):
         _send(p.stdin, (7, 2, req2))
         _, _, out2 = _recv(rf)
         assert "pred_frames" not in out2 and sorted(os.listdir(tmp_path / "c")) == sorted([f"{i}.jpg" for i in range(8)] + ["action_seq.json"])
-        # a malformed request must not kill the worker: well-formed zero frames come back
-        bad = {"b_action": b_action[:1], "b_image": b_image[:1], "save_dirs": ["x"], "request_model_name": "cosmos", "return_objects": [True]}
+        # a request whose DATA cannot be served (no b_image and no cond_rgb.png on disk) is absorbed: well-formed zero frames
+        # plus an explicit per-branch `errors` list; the worker keeps serving
+        bad = {"b_action": b_action[:1], "save_dirs": [str(tmp_path / "missing")], "request_model_name": "igen", "return_objects": [True]}
         _send(p.stdin, (7, 3, bad))
         _, _, out3 = _recv(rf)
         assert out3["pred_frames"].shape == (1, 8, 3, 40, 48) and int(out3["pred_frames"].max()) == 0
-        _send(p.stdin, "DONE")
+        assert isinstance(out3["errors"], list) and len(out3["errors"]) == 1 and "cond_rgb" in out3["errors"][0]
+        _send(p.stdin, (7, 4, req1))
+        _, _, out4 = _recv(rf)
+        assert out4["pred_frames"].std() > 1.0 and "errors" not in out4
+        # an observation that is not 576x1024-shaped (the solvers send 384x384 / 480x480) goes through the LANCZOS branch
+        req5 = {**req1, "b_image": rng.integers(0, 256, size=(1, 3, 48, 48), dtype=np.uint8)}
+        _send(p.stdin, (7, 5, req5))
+        _, _, out5 = _recv(rf)
+        assert out5["pred_frames"].shape == (1, 8, 3, 40, 48) and out5["pred_frames"].std() > 1.0
+        # a request for ANOTHER model is a configuration error: the worker dies loudly like the reference's (api_models/__init__.py:189)
+        _send(p.stdin, (7, 6, {**req1, "request_model_name": "cosmos"}))
         p.stdin.close()
-        assert p.wait(timeout=60) == 0
+        assert p.wait(timeout=60) != 0
     finally:
         if p.poll() is None:
             p.kill()

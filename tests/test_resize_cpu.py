@@ -16,6 +16,14 @@ def test_numpy_twin_matches_pil(H, W, ow, oh):
     assert np.array_equal(R.resize_reference(img, ow, oh), ref)
 
 
+@pytest.mark.parametrize("H,W,ow,oh", [(480, 480, 1024, 576), (384, 384, 1024, 576), (64, 128, 48, 40), (17, 23, 40, 31), (576, 1024, 1024, 576)])
+def test_numpy_twin_matches_pil_lanczos(H, W, ow, oh):
+    """The request side: video_processor.preprocess resizes the conditioning image with PIL LANCZOS (DP/image_processor.py:501)."""
+    img = np.random.default_rng(H * W + 1).integers(0, 256, (H, W, 3), dtype=np.uint8)
+    ref = np.asarray(Image.fromarray(img).resize((ow, oh), Image.LANCZOS))
+    assert np.array_equal(R.resize_reference(img, ow, oh, "lanczos"), ref)
+
+
 def test_requant_lut_matches_reference_chain():
     from torchvision.transforms.functional import to_tensor
     img = Image.fromarray(np.arange(256, dtype=np.uint8).reshape(16, 16))

@@ -36,8 +36,11 @@ def _run(rank, world, port, tmp, q):
     worker._resizer_key = (args.height, args.width, args.out_height, args.out_width)
     worker._resizer = S.cpu_resizer(args)
     if rank > 0:
-        worker.helper_loop()
-        q.put((rank, True))
+        try:
+            worker.helper_loop()
+            q.put((rank, False))                                 # the last request of rank 0's script must end every rank
+        except RuntimeError:
+            q.put((rank, True))
         dist.destroy_process_group()
         return
     ok = True
@@ -55,14 +58,24 @@ def _run(rank, world, port, tmp, q):
     out = worker.do_some_tasks(req)                               # files mode: every rank writes its own branches
     ok &= "pred_frames" not in out and all(sorted(os.listdir(d)) == sorted([f"{t}.jpg" for t in range(8)] + ["action_seq.json"])
                                              for d in req["save_dirs"])
-    bad = worker.do_some_tasks({**req, "request_model_name": "cosmos", "return_objects": [True] * 3})
-    ok &= bad["pred_frames"].shape == (3, 8, 3, 20, 24) and int(bad["pred_frames"].max()) == 0      # all ranks reject alike: no hang
-    acts_bad = acts.copy()
-    acts_bad[1] = [4, 73, 0, 0, 0, 0, 0, 0]                       # branch 1 lives on rank 1 and raises there only
-    out = worker.do_some_tasks({**req, "b_action": acts_bad, "return_objects": [True] * 3})
-    ok &= out["pred_frames"].shape == (3, 8, 3, 20, 24) and int(out["pred_frames"].max()) == 0      # agreed failure, no hang in the gather
+    # data error (no b_image, no cond_rgb.png): every rank absorbs it alike -- zero frames + an explicit `errors` list, no hang
+    nofile = {k: v for k, v in req.items() if k != "b_image"}
+    bad = worker.do_some_tasks({**nofile, "return_objects": [True] * 3})
+    ok &= bad["pred_frames"].shape == (3, 8, 3, 20, 24) and int(bad["pred_frames"].max()) == 0 and len(bad["errors"]) == 3
     out = worker.do_some_tasks({**req, "return_objects": [True] * 3})                                   # and the worker keeps serving
-    ok &= int(out["pred_frames"][2].max()) == _expected(acts[2], 7)
+    ok &= int(out["pred_frames"][2].max()) == _expected(acts[2], 7) and "errors" not in out
+    # a library-side failure on ONE rank (branch 1 lives on rank 1 and raises there only) is fatal on EVERY rank: agreed before
+    # the all-gather, so nobody hangs and nobody returns black frames
+    acts_bad = acts.copy()
+    acts_bad[1] = [4, 73, 0, 0, 0, 0, 0, 0]
+    try:
+        worker.do_some_tasks({**req, "b_action": acts_bad, "return_objects": [True] * 3})
+        ok = False
+    except RuntimeError:
+        pass
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+    return
     worker.serve_request(None)                                    # shutdown broadcast
     q.put((rank, bool(ok)))
     dist.destroy_process_group()

@@ -10,17 +10,27 @@ static thread_local std::string g_last_error;
 
 void set_last_error(const std::string& msg) { g_last_error = msg; }
 
+int current_device() {
+    int dev = 0;
+    return cudaGetDevice(&dev) == cudaSuccess ? dev : 0;
+}
+
+// per-device cache: one process may drive engines on several GPUs
 int num_sms() {
-    static int cached = 0;
-    if (cached == 0) {
-        int dev = 0, n = 0;
-        if (cudaGetDevice(&dev) == cudaSuccess &&
-            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
-            cached = n;
-        else
-            cached = 148;
+    static int cached[64] = {0};
+    const int dev = current_device() & 63;
+    if (cached[dev] == 0) {
+        int n = 0;
+        cached[dev] = (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) ? n : 148;
     }
-    return cached;
+    return cached[dev];
+}
+
+bool first_call_on_device(unsigned long long* mask) {
+    const unsigned long long bit = 1ull << (current_device() & 63);
+    if (*mask & bit) return false;
+    *mask |= bit;
+    return true;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,

@@ -48,7 +48,8 @@ __device__ __forceinline__ float fast_exp2(float x) {
 // 2^x for x <= ~2 on the FMA/ALU pipes (Cody-Waite split + degree-3 minimax, max rel. error 7.5e-5 -- below the
 // fp16 rounding of P).  Offloads part of the exponentials from the MUFU pipe, which bounds the softmax warps.
 __device__ __forceinline__ float exp2_poly(float x) {
-    x = fmaxf(x, -24.0f);                              // below fp16's smallest subnormal anyway
+    x = fmaxf(x, -26.0f);                              // 2^-26 rounds to +0 in the fp16 pack (half of the smallest subnormal is 2^-25):
+                                                       // masked (-inf) and strongly negative scores contribute exactly 0, like MUFU.EX2
     const float xr = x + 12582912.0f;                  // 1.5 * 2^23: round(x) lands in the low mantissa bits
     const float f = x - (xr - 12582912.0f);            // in [-0.5, 0.5]
     const float p = fmaf(fmaf(fmaf(0.05517167f, f, 0.24261113f), f, 0.69326097f), f, 0.99992806f);
@@ -399,12 +400,11 @@ extern "C" int wiw_attention_spatial(const void* qkv, void* out, int images, int
     a.S = S;
     a.nkv = (S + kKV - 1) / kKV;
     a.scale_log2 = 0.125f * 1.4426950408889634f;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static unsigned long long attr_set = 0;
+    if (first_call_on_device(&attr_set)) {
         WIW_CHECK_CUDA(cudaFuncSetAttribute(attn_spatial_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
         WIW_CHECK_CUDA(cudaFuncSetAttribute(attn_spatial_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
         WIW_CHECK_CUDA(cudaFuncSetAttribute(attn_spatial_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
-        attr_set = true;
     }
     // share of the exponentials evaluated on the FMA pipe instead of MUFU (development aid for A/B runs; see exp2_poly)
     static const int poly = getenv("WIW_ATTN_POLY") ? atoi(getenv("WIW_ATTN_POLY")) : 1;       // A/B on B200: 1 of 4 pairs on the FMA pipe = +6 % at S=9216; 2 of 4 = -4 %

@@ -32,7 +32,11 @@ void set_last_error(const std::string& msg);          // defined in wiw_api.cu
         }                                                                                          \
     } while (0)
 
-int num_sms();                                        // cached cudaDevAttrMultiProcessorCount
+int current_device();
+int num_sms();                                        // cudaDevAttrMultiProcessorCount of the CURRENT device (cached per device)
+// true exactly once per (mask, current device): guards per-device one-time setup such as
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize), which is a per-device function attribute
+bool first_call_on_device(unsigned long long* mask);
 
 // Encode a tiled TMA descriptor (driver entry point resolved at run time; the library does
 // not link libcuda so it still loads on a CPU-only box).  Returns 0 on success.

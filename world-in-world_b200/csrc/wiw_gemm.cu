@@ -578,15 +578,14 @@ static int launch_conv_gemm(const wiw_gemm_desc* d, cudaStream_t stream) {
     if (d->res) { if (enc_out(&tm_res, d->res, d->res_stride, false)) return 3; } else tm_res = tm_out;
     if (d->aux) { if (enc_out(&tm_aux, d->aux, d->aux_stride, false)) return 3; } else tm_aux = tm_out;
 
-    static bool attr_set = false;
-    if (!attr_set) {
+    static unsigned long long attr_set = 0;
+    if (first_call_on_device(&attr_set)) {
         WIW_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
         WIW_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
         WIW_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
         WIW_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
         WIW_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
         WIW_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
-        attr_set = true;
     }
     if (cg == 1) {
         int grid = num_sms();

@@ -155,10 +155,9 @@ extern "C" int wiw_attention_temporal_mma(const void* qkv, void* out, int B, int
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     WIW_REQUIRE(qkv && out && C % 64 == 0 && F >= 1 && F <= 16, "bad args");
     const size_t smem = (size_t)kTaWarps * 3 * kTaTile * sizeof(__half);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static unsigned long long attr_set = 0;
+    if (first_call_on_device(&attr_set)) {
         WIW_CHECK_CUDA(cudaFuncSetAttribute(temporal_attn_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
     }
     const long long problems = (long long)B * S * (C / 64);
     long long blocks = (problems + kTaWarps - 1) / kTaWarps;

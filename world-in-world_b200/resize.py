@@ -1,4 +1,4 @@
-"""Pillow-exact bicubic resize of uint8 frames on the GPU.
+"""Pillow-exact resize (BICUBIC and LANCZOS) of uint8 frames on the GPU.
 
 The reference post-processes every generated frame on the CPU with `img.resize(save_size, Image.BICUBIC)`
 (downstream/api_models/__init__.py:159) and then quantises twice (to_tensor /255 -> (clip*255).astype(uint8),
@@ -7,6 +7,11 @@ The reference post-processes every generated frame on the CPU with `img.resize(s
 vertical pass with an 8-bit intermediate.  `coefficients()` restates that table construction (validated bit-exact
 against PIL in tests/test_resize_cpu.py); the two passes run in wiw_resize_bicubic_u8 as integer MACs, so the GPU
 result equals PIL's byte for byte.
+
+The same resampler with Pillow's LANCZOS window (support 3, sinc(x) sinc(x/3)) serves the request side: the reference's
+`video_processor.preprocess(image, height, width)` resizes the conditioning PIL image with `resample="lanczos"` in uint8
+before the VAE encode (DP/image_processor.py:118,501; pipeline :520), so observations that are not already 576x1024
+(the solvers send 384x384 / 480x480) take that path here too, byte for byte.
 """
 from __future__ import annotations
 
@@ -24,12 +29,26 @@ def _bicubic(x: np.ndarray, a: float = -0.5) -> np.ndarray:
     return np.where(x < 1.0, ((a + 2.0) * x - (a + 3.0)) * x * x + 1, np.where(x < 2.0, (((x - 5) * x + 8) * x - 4) * a, 0.0))
 
 
-@lru_cache(maxsize=32)
-def coefficients(in_size: int, out_size: int) -> Tuple[np.ndarray, np.ndarray]:
+def _lanczos(x: np.ndarray) -> np.ndarray:
+    """Pillow's lanczos_filter: sinc(x) * sinc(x / 3) on [-3, 3), sinc(x) = sin(pi x) / (pi x) evaluated in double."""
+    def sinc(v):
+        v = np.asarray(v, np.float64) * np.pi
+        with np.errstate(invalid="ignore", divide="ignore"):
+            return np.where(v == 0.0, 1.0, np.sin(v) / v)
+    x = np.asarray(x, np.float64)
+    return np.where((x >= -3.0) & (x < 3.0), sinc(x) * sinc(x / 3.0), 0.0)
+
+
+FILTERS = {"bicubic": (_bicubic, 2.0), "lanczos": (_lanczos, 3.0)}
+
+
+@lru_cache(maxsize=64)
+def coefficients(in_size: int, out_size: int, filt: str = "bicubic") -> Tuple[np.ndarray, np.ndarray]:
     """(bounds int32 [out, 2] = (first source index, tap count), kk int32 [out, ksize]) of Pillow's precompute_coeffs."""
+    fn, base_support = FILTERS[filt]
     scale = in_size / out_size
     filterscale = max(scale, 1.0)
-    support = 2.0 * filterscale
+    support = base_support * filterscale
     ksize = int(np.ceil(support)) * 2 + 1
     bounds = np.zeros((out_size, 2), np.int32)
     kk = np.zeros((out_size, ksize), np.int32)
@@ -38,7 +57,7 @@ def coefficients(in_size: int, out_size: int) -> Tuple[np.ndarray, np.ndarray]:
         center = (xx + 0.5) * scale
         xmin = max(int(center - support + 0.5), 0)
         xmax = min(int(center + support + 0.5), in_size) - xmin
-        w = _bicubic((np.arange(xmax) + xmin - center + 0.5) * ss)
+        w = fn((np.arange(xmax) + xmin - center + 0.5) * ss)
         ww = 0.0
         for v in w:                       # Pillow accumulates the normaliser sequentially in double
             ww += float(v)
@@ -56,10 +75,10 @@ def requant_lut() -> np.ndarray:
     return (np.clip(x, 0, 1) * 255).astype(np.uint8)
 
 
-def resize_reference(img: np.ndarray, out_w: int, out_h: int) -> np.ndarray:
+def resize_reference(img: np.ndarray, out_w: int, out_h: int, filt: str = "bicubic") -> np.ndarray:
     """Pure-numpy evaluation of the two passes (img [H, W, C] uint8) -- the CPU twin of the CUDA kernel, used by tests."""
     H, W, C = img.shape
-    bh, kh = coefficients(W, out_w)
+    bh, kh = coefficients(W, out_w, filt)
     tmp = np.zeros((H, out_w, C), np.uint8)
     for xx in range(out_w):
         x0, n = bh[xx]
@@ -67,7 +86,7 @@ def resize_reference(img: np.ndarray, out_w: int, out_h: int) -> np.ndarray:
         for x in range(n):
             acc += img[:, x0 + x, :].astype(np.int64) * int(kh[xx, x])
         tmp[:, xx, :] = np.clip(acc >> PRECISION_BITS, 0, 255)
-    bv, kv = coefficients(H, out_h)
+    bv, kv = coefficients(H, out_h, filt)
     out = np.zeros((out_h, out_w, C), np.uint8)
     for yy in range(out_h):
         y0, n = bv[yy]
@@ -79,13 +98,15 @@ def resize_reference(img: np.ndarray, out_w: int, out_h: int) -> np.ndarray:
 
 
 class GpuResizer:
-    """uint8 planes [P, H, W] on the device -> [P, out_h, out_w], Pillow BICUBIC + optional requantisation LUT."""
+    """uint8 planes [P, H, W] on the device -> [P, out_h, out_w], Pillow BICUBIC / LANCZOS + optional requantisation LUT."""
 
-    def __init__(self, H: int, W: int, out_h: int, out_w: int, device, requant: bool = True):
+    def __init__(self, H: int, W: int, out_h: int, out_w: int, device, requant: bool = True, filt: str = "bicubic"):
         self.shape = (H, W, out_h, out_w)
-        bh, kh = coefficients(W, out_w)
-        bv, kv = coefficients(H, out_h)
+        bh, kh = coefficients(W, out_w, filt)
+        bv, kv = coefficients(H, out_h, filt)
         dev = torch.device(device)
+        if dev.type == "cuda" and dev.index is None:          # "cuda" and "cuda:0" must compare equal below
+            dev = torch.device("cuda", torch.cuda.current_device())
         self.bh, self.kh = torch.from_numpy(bh.copy()).to(dev), torch.from_numpy(kh.copy()).to(dev)
         self.bv, self.kv = torch.from_numpy(bv.copy()).to(dev), torch.from_numpy(kv.copy()).to(dev)
         self.lut = torch.from_numpy(requant_lut() if requant else np.arange(256, dtype=np.uint8)).to(dev)
@@ -95,7 +116,9 @@ class GpuResizer:
         from . import lib as L
         lib = L.require_device()
         H, W, oh, ow = self.shape
-        assert planes.dtype == torch.uint8 and planes.device == self.device and planes.is_contiguous() and planes.shape[-2:] == (H, W)
+        if planes.dtype != torch.uint8 or planes.device != self.device or not planes.is_contiguous() or planes.shape[-2:] != (H, W):
+            raise L.WiwError(f"GpuResizer({H}x{W} on {self.device}) got {planes.dtype} {tuple(planes.shape)} on {planes.device} "
+                             f"contiguous={planes.is_contiguous()}")
         P = planes.numel() // (H * W)
         tmp = torch.empty(P, H, ow, dtype=torch.uint8, device=self.device)
         out = torch.empty(*planes.shape[:-2], oh, ow, dtype=torch.uint8, device=self.device)

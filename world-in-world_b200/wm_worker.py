@@ -15,8 +15,13 @@ Deliberate deviations from the shipped reference, each fixing a latent defect li
   - world_model_name is defined ("igen", downstream/vlm.py:31) and a name sliced by the manager's Batcher
     (worker_manager.py:457-458: "i", "g", "e", "n", "" ...) is accepted when it is a contiguous slice of it;
   - RGBA observations are sliced to RGB (the reference pipeline fails on 4-channel PIL images);
-  - an exception inside the task is caught, logged and answered with well-formed zero frames instead of
-    killing the worker (the manager has no error channel, worker_manager.py:369-379).
+  - a per-request DATA error (unreadable cond_rgb.png, malformed image / action arrays) is logged to stderr and answered
+    with a well-formed reply that carries an explicit `errors` list (one message per branch; zero frames in
+    return_objects mode) -- the manager has no error channel (worker_manager.py:369-379) and merges replies key by key
+    with list.extend (:476-487), so a per-branch list survives the Batcher.  Everything else -- a wrong
+    request_model_name, a failed check_inputdict, a WiwError, any CUDA error (sticky: every later request would
+    silently return black frames) -- re-raises and ends the worker loudly, as the reference worker does; so do
+    MAX_CONSECUTIVE_DATA_ERRORS data errors in a row.
 """
 from __future__ import annotations
 
@@ -34,6 +39,12 @@ import numpy as np
 import torch
 
 WORLD_MODEL_NAME = "igen"
+MAX_CONSECUTIVE_DATA_ERRORS = 3
+
+
+class RequestDataError(Exception):
+    """The request's own data cannot be served (missing / unreadable image file, malformed arrays).  The only error class a
+    worker absorbs; configuration, library and device errors propagate."""
 IGENEX_ACTION_IDS = {"forward": 1, "turn_left": 2, "turn_right": 3, "stop": 4, "placeholder": 0}
 
 
@@ -216,11 +227,18 @@ class Navigator:
         F, H, W = self.num_frames, self.image_height, self.image_width
         sched = EulerSchedule(self.num_inference_steps)
         out = torch.empty((b, F, 3, H, W), dtype=torch.uint8, device=dev)
-        img = torch.from_numpy(images_u8[:, :3]).to(dev).float() / 255.0                    # pil_to_numpy/numpy_to_pt: [0,1]
-        if img.shape[-2:] != (H, W):
-            img = torch.nn.functional.interpolate(img, size=(H, W), mode="bilinear", antialias=True)
-        emb = frontend.encode_image_clip(img, self.image_encoder)                             # [b, 1, D]
-        pre = img * 2.0 - 1.0                                                                # video_processor.preprocess
+        # The reference feeds the observation AS SENT (384x384 / 480x480 from the solvers) to _encode_image, whose antialiased
+        # resize goes straight to 224x224 (pipeline :192-200), and separately resizes the PIL image to (W, H) with LANCZOS in
+        # uint8 for the VAE branch (video_processor.preprocess, DP/image_processor.py:501; pipeline :520).
+        obs = torch.from_numpy(np.ascontiguousarray(images_u8[:, :3])).to(dev)               # uint8 [b, 3, Hin, Win]
+        emb = frontend.encode_image_clip(obs.float() / 255.0, self.image_encoder)             # pil_to_numpy/numpy_to_pt: [0,1]; [b, 1, D]
+        if tuple(obs.shape[-2:]) != (H, W):
+            key = (int(obs.shape[-2]), int(obs.shape[-1]), H, W)
+            if getattr(self, "_obs_resizer_key", None) != key:
+                from .resize import GpuResizer
+                self._obs_resizer, self._obs_resizer_key = GpuResizer(*key, device=dev, requant=False, filt="lanczos"), key
+            obs = self._obs_resizer(obs)
+        pre = (obs.float() / 255.0) * 2.0 - 1.0                                              # video_processor.preprocess: normalize
         if seeds is not None:
             # sharded serving: one generator state per branch, so a branch's noise does not depend on which rank rolls it out
             gens = [torch.Generator(device=dev).manual_seed(int(sd)) for sd in seeds]
@@ -266,35 +284,63 @@ class WorldModelWorker:
             self._resizer, self._resizer_key = GpuResizer(*key, device=frames.device), key
         return self._resizer(frames)
 
-    def do_some_tasks(self, input_dict: dict) -> dict:
-        save_dirs = list(input_dict.get("save_dirs", []))
+    def _validate(self, input_dict: dict) -> None:
+        """Configuration-level checks: a failure here is not a data error and ends the worker (the reference asserts too,
+        api_models/__init__.py:189, worker_manager.py:106-134)."""
+        check_inputdict(input_dict)
+        if not name_matches(input_dict["request_model_name"], WORLD_MODEL_NAME):
+            raise ValueError(f"request_model_name: {input_dict['request_model_name']} does not match deployed world_model_name: "
+                             f"{WORLD_MODEL_NAME}")
+
+    @staticmethod
+    def _request_arrays(input_dict: dict, save_dirs: List[str]):
+        """b_action / b_image of a validated request; anything wrong with the DATA raises RequestDataError."""
         try:
-            check_inputdict(input_dict)
-            assert name_matches(input_dict["request_model_name"], WORLD_MODEL_NAME), \
-                f"request_model_name: {input_dict['request_model_name']} does not match deployed world_model_name: {WORLD_MODEL_NAME}"
             b_action = np.asarray(input_dict["b_action"])
-            return_objects = bool(input_dict.get("return_objects"))
             b_image = input_dict.get("b_image")
             if b_image is None:
                 from PIL import Image
                 b_image = np.stack([np.asarray(Image.open(os.path.join(d, "cond_rgb.png")).convert("RGB")).transpose(2, 0, 1)
                                     for d in save_dirs])
-            assert b_image.ndim == 4 and b_image.dtype == np.uint8, f"b_image should be uint8 B C H W, got {b_image.shape}"
-            assert len(b_action) == len(save_dirs)
-            action_ids = action_ids_idx_encode(b_action)
-            frames = self.nav.inference(action_ids, b_image, self.args.out_width, self.args.out_height, on_device=True)
-            if return_objects:
-                # only the 480x480 uint8 result crosses PCIe
-                return {"pred_frames": self.resized_frames(frames).cpu().numpy(), "save_dirs": save_dirs}
-            # files mode (saver.py:221-274): same device-side resize + requantisation, the JPEGs hold exactly the bytes the reference's
-            # images_to_tensor -> save_predict chain would write
-            save_predict_u8(self.resized_frames(frames).cpu().numpy(), b_action, save_dirs)
-            return {"save_dirs": save_dirs}
-        except Exception:                       # never die inside task_fn (SURVEY.md 8b "Errors")
-            traceback.print_exc()
-            n = len(save_dirs)
-            zeros = np.zeros((n, self.args.num_frames, 3, self.args.out_height, self.args.out_width), dtype=np.uint8)
-            return {"pred_frames": zeros, "save_dirs": save_dirs}
+        except (OSError, ValueError) as e:
+            raise RequestDataError(f"cannot read the request's observation / actions: {e!r}") from e
+        if b_image.ndim != 4 or b_image.dtype != np.uint8 or b_image.shape[1] not in (3, 4):
+            raise RequestDataError(f"b_image should be uint8 B C H W with 3 or 4 channels, got {b_image.dtype} {b_image.shape}")
+        if b_action.ndim != 2 or len(b_action) != len(save_dirs) or len(b_image) != len(save_dirs):
+            raise RequestDataError(f"b_action {b_action.shape} / b_image {b_image.shape} do not match {len(save_dirs)} save_dirs")
+        return b_action, b_image
+
+    def _data_error_reply(self, err: Exception, save_dirs: List[str], return_objects: bool) -> dict:
+        """Well-formed reply for an absorbed data error, with an explicit marker: `errors` (one message per branch)."""
+        self._consecutive_data_errors = getattr(self, "_consecutive_data_errors", 0) + 1
+        print(f"[igenex worker] REQUEST FAILED ({self._consecutive_data_errors} in a row): {err}", file=sys.stderr, flush=True)
+        if self._consecutive_data_errors >= MAX_CONSECUTIVE_DATA_ERRORS:
+            raise RuntimeError(f"{self._consecutive_data_errors} consecutive failed requests; last: {err}") from err
+        n = len(save_dirs)
+        out = {"save_dirs": save_dirs, "errors": [str(err)] * n}
+        if return_objects:
+            out["pred_frames"] = np.zeros((n, self.args.num_frames, 3, self.args.out_height, self.args.out_width), dtype=np.uint8)
+        return out
+
+    def do_some_tasks(self, input_dict: dict) -> dict:
+        self._validate(input_dict)                                  # raises: not a per-request data problem
+        save_dirs = list(input_dict["save_dirs"])
+        return_objects = bool(input_dict.get("return_objects"))
+        try:
+            b_action, b_image = self._request_arrays(input_dict, save_dirs)
+        except RequestDataError as e:
+            return self._data_error_reply(e, save_dirs, return_objects)
+        # from here on every failure is the library's or the device's (WiwError, CUDA): it propagates and ends the worker
+        action_ids = action_ids_idx_encode(b_action)
+        frames = self.nav.inference(action_ids, b_image, self.args.out_width, self.args.out_height, on_device=True)
+        small = self.resized_frames(frames).cpu().numpy()           # only the 480x480 uint8 result crosses PCIe
+        self._consecutive_data_errors = 0
+        if return_objects:
+            return {"pred_frames": small, "save_dirs": save_dirs}
+        # files mode (saver.py:221-274): same device-side resize + requantisation, the JPEGs hold exactly the bytes the reference's
+        # images_to_tensor -> save_predict chain would write
+        save_predict_u8(small, b_action, save_dirs)
+        return {"save_dirs": save_dirs}
 
 
 class ShardedWorldModelWorker(WorldModelWorker):
@@ -340,24 +386,14 @@ class ShardedWorldModelWorker(WorldModelWorker):
         self.serial += 1
         F, Ho, Wo = self.args.num_frames, self.args.out_height, self.args.out_width
         dev = self.nav.device
-        n_req = len(req.get("save_dirs", [])) if isinstance(req, dict) else 0
-
-        def failed() -> dict:                             # the manager has no error channel: well-formed zero frames
-            zeros = np.zeros((n_req, F, 3, Ho, Wo), dtype=np.uint8)
-            return {"pred_frames": zeros, "save_dirs": list(req.get("save_dirs", [])) if isinstance(req, dict) else []}
-
-        ok, b, idx, loc, acts, small = True, 0, [], {}, None, None
+        # outcome per rank: 0 ok, 1 data error (absorbed: explicit `errors` reply), 2 anything else (fatal on EVERY rank)
+        status, err, b, idx, loc, acts, small = 0, None, 0, [], {}, None, None
+        return_objects = bool(req.get("return_objects")) if isinstance(req, dict) else False
         try:
-            check_inputdict(req)
-            assert name_matches(req["request_model_name"], WORLD_MODEL_NAME), f"request_model_name: {req['request_model_name']}"
+            self._validate(req)
             b, idx, loc = self._local(req)
             if idx:
-                b_image = loc.get("b_image")
-                if b_image is None:
-                    from PIL import Image
-                    b_image = np.stack([np.asarray(Image.open(os.path.join(d, "cond_rgb.png")).convert("RGB")).transpose(2, 0, 1)
-                                        for d in loc["save_dirs"]])
-                acts = np.asarray(loc["b_action"])
+                acts, b_image = self._request_arrays(loc, loc["save_dirs"])
                 seeds = [1 + 1000003 * self.serial + i for i in idx]          # per (request, branch): independent of the rank count
                 frames = self.nav.inference(action_ids_idx_encode(acts), b_image, Wo, Ho, on_device=True, seeds=seeds,
                                             cfg_split_group=self.pair_group if self._use_pairs(b) else None)
@@ -365,25 +401,28 @@ class ShardedWorldModelWorker(WorldModelWorker):
             else:
                 acts = np.zeros((0, F), np.int64)
                 small = torch.zeros((0, F, 3, Ho, Wo), dtype=torch.uint8, device=dev)
-        except Exception:
+        except RequestDataError as e:
+            status, err = 1, e
+        except Exception as e:
             traceback.print_exc()
-            ok = False
+            status, err = 2, e
         # one rank failing must not leave the others waiting in the all-gather: agree on the outcome first (control plane, gloo)
-        flag = torch.tensor([1 if ok else 0], dtype=torch.int32)
-        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-        if int(flag.item()) == 0:
-            return failed()
-        try:
-            if bool(req.get("return_objects")):
-                out = (gather_frames_pairs if self._use_pairs(b) else gather_frames)(small, b)      # the one data-path collective
-                return {"pred_frames": out.cpu().numpy(), "save_dirs": list(req["save_dirs"])} if self.rank == 0 else {}
-            if idx and not (self._use_pairs(b) and self.rank % 2):             # files mode: every rank (pair leader) writes its own branches
-                save_predict_u8(small.cpu().numpy(), acts, loc["save_dirs"])
-            dist.barrier()
-            return {"save_dirs": list(req["save_dirs"])} if self.rank == 0 else {}
-        except Exception:
-            traceback.print_exc()
-            return failed()
+        flag = torch.tensor([status], dtype=torch.int32)
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+        worst = int(flag.item())
+        if worst == 2:                                    # configuration / library / device error somewhere: every rank stops
+            raise RuntimeError(f"rank {self.rank}: request {self.serial} failed fatally on some rank") from err
+        if worst == 1:
+            msg = err if err is not None else RequestDataError("the request's data could not be served on another rank")
+            return self._data_error_reply(msg, list(req.get("save_dirs", [])), return_objects)
+        self._consecutive_data_errors = 0
+        if return_objects:
+            out = (gather_frames_pairs if self._use_pairs(b) else gather_frames)(small, b)      # the one data-path collective
+            return {"pred_frames": out.cpu().numpy(), "save_dirs": list(req["save_dirs"])} if self.rank == 0 else {}
+        if idx and not (self._use_pairs(b) and self.rank % 2):             # files mode: every rank (pair leader) writes its own branches
+            save_predict_u8(small.cpu().numpy(), acts, loc["save_dirs"])
+        dist.barrier()
+        return {"save_dirs": list(req["save_dirs"])} if self.rank == 0 else {}
 
     def do_some_tasks(self, input_dict: dict) -> dict:            # rank 0's task_fn
         return self.serve_request(input_dict)
