@@ -99,7 +99,7 @@ class ClockSampler:
 def cpu_reference_sample(steps: int, warmup: int, max_forwards: int = 8):
     """The reference's CPU implementation of the path = the oracle port (the vendored fork itself lives under
     /root/reference, which does not exist on the GPU box).  Bounded sample: UNet forwards of the full
-    1.53 B-parameter architecture (CFG pair x 14 frames) at 36x64 latents (a quarter of 72x128 in each... half per axis),
+    1.53 B-parameter architecture (CFG pair x 14 frames) at 40x64 latents (28 % of the 72x128 pixels),
     fp32, on the host threads a short sweep finds fastest; frames/sec of the named workload is extrapolated by the
     algorithmic-FLOP ratio.  `steps` forwards are requested; at most `max_forwards` are timed so that the run stays bounded."""
     from torch.utils.flop_counter import FlopCounterMode
@@ -142,7 +142,7 @@ def cpu_reference_sample(steps: int, warmup: int, max_forwards: int = 8):
                 break                                                           # already on the wrong side of the optimum
         cores = min(sweep, key=sweep.get)
         torch.set_num_threads(cores)
-        sh, sw = 36, 64
+        sh, sw = 40, 64                                                    # multiples of 8: three stride-2 levels
         x = torch.randn(2, F, 8, sh, sw, generator=g)
         with FlopCounterMode(display=False) as fc:
             w0 = fwd(x)                                                         # counted pass doubles as the warm-up at this size

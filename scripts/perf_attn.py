@@ -51,7 +51,7 @@ def sdpa_rows():
         print(f"flash_attn: unavailable ({str(e).splitlines()[0][:120]})", flush=True)
 
 
-if "sdpa" in sys.argv or "attn" in sys.argv:
+if ("sdpa" in sys.argv or "attn" in sys.argv) and "nosdpa" not in sys.argv:
     sdpa_rows()
 NORM_ONLY = "norm" in sys.argv
 ATTN_ONLY = "attn" in sys.argv

@@ -375,6 +375,614 @@ attn_spatial_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
     }
 }
 
+
+// =====================================================================================================================
+// TS-mode variant: both A operands of the two GEMMs live in TENSOR MEMORY, so the only shared-memory operand traffic
+// of the tensor pipe is the K / V tile itself.
+//
+// Why: a tcgen05.mma reads its shared-memory operands at ~64 B per cycle per SM (profiles/r02_mma_cost_v2.txt).  With A and B
+// both in shared memory an M128 N128 K16 `Q K^T` step moves 4 KB + 4 KB = 128 cycles for 64 cycles of tensor work, a
+// `P V` step (N = 80) 4 KB + 2.5 KB = 102 cycles for 40: the SS kernel above spends 2 x (4 x 128 + 8 x 102) = 2 656 cycles per KV
+// tile on operand fetch (measured: 2 960 per iteration) while the tensor pipe is busy for 1 152.  Here
+//   * Q_t is copied once per CTA from its TMA tile into TMEM (32 columns per tile) by the softmax threads;
+//   * P_t is written by the softmax threads straight into TMEM with tcgen05.st, packed fp16, ALIASED onto the first 64 columns
+//     of its own S_t (a thread only overwrites score columns it has already read: P chunk c lands in columns [16c, 16c+16),
+//     inside score chunks <= c/2);
+// so `Q K^T` fetches 4 KB (64 cycles = its tensor time) and `P V` 2.5 KB (40 cycles = its tensor time) per instruction.
+// The tensor pipe executes one thread's MMAs in issue order, so the MMA warp issues PV(t, j) and then QK(t, j+1) -- which
+// overwrites S_t / P_t -- back to back without waiting in between, and the single commit after QK(t, j+1) tells the softmax
+// threads both that S_t(j+1) is ready and that O_t is idle again (PV(t, j) retired): no separate "S free" / "PV done" barriers.
+//
+// TMEM columns (every operand starts on a multiple of 32): S0|P0 [0,128)  S1|P1 [128,256)  O0 [256,336)  Q0 [352,384)  O1 [384,464)  Q1 [480,512)
+constexpr int kRingTS = 6;
+constexpr int kAttnSmemTS = 1024 + kTileBytes * (2 + kRingTS + 1) + 256;    // Q0,Q1 (later: O staging) | K/V ring | ones
+constexpr uint32_t kColO = 256, kColQ = 352, kColStride = 128;     // tile t: O at kColO + t*128, Q at kColQ + t*128
+
+// 32 scores -> 16 packed fp16x2 probabilities p = 2^(s*c - mc); word i = (key 2i | key 2i+1 << 16)
+template <int kPolyPairs>
+__device__ __forceinline__ void exp_pack(const uint32_t* r, float c, float mc, uint32_t* p) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const float a0 = fmaf(__uint_as_float(r[2 * i]), c, -mc);
+        const float a1 = fmaf(__uint_as_float(r[2 * i + 1]), c, -mc);
+        if ((i & 3) < kPolyPairs) p[i] = cvt_f16x2(exp2_poly(a0), exp2_poly(a1));
+        else p[i] = cvt_f16x2(fast_exp2(a0), fast_exp2(a1));
+    }
+}
+
+template <int POLY>
+__global__ void __launch_bounds__(kAttnThreads, 1)
+attn_spatial_ts_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_out,
+                       const __grid_constant__ AttnArgs a, int C) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t sQ = base;                                    // 2 tiles; reused as the O staging tiles of the epilogue
+    const uint32_t sRing = sQ + 2 * kTileBytes;
+    const uint32_t sOnes = sRing + kRingTS * kTileBytes;         // [128][64] fp16 ones: the extra N-atom of the PV B operand
+    const uint32_t bars = sOnes + kTileBytes;
+    const uint32_t bar_q = bars;
+    const uint32_t bar_full = bars + 8;                          // [kRingTS]
+    const uint32_t bar_empty = bar_full + 8 * kRingTS;           // [kRingTS]
+    const uint32_t bar_s_full = bar_empty + 8 * kRingTS;         // [2]  S_t(j) written, O_t idle
+    const uint32_t bar_p_full = bar_s_full + 16;                 // [2]  P_t(j) in TMEM, S_t(j) fully read
+    const uint32_t bar_q_ready = bar_p_full + 16;                // [2]  Q_t copied into TMEM
+    const uint32_t bar_o_done = bar_q_ready + 16;                // [2]  last PV of tile t retired
+    const uint32_t tmem_slot = bar_o_done + 16;
+    uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));       // generic pointer to `base`
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q0 = blockIdx.x * 2 * kQ, head = blockIdx.y, img = blockIdx.z;
+    const int nkv = a.nkv;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tm_qkv);
+        tma_prefetch_desc(&tm_out);
+        mbar_init(bar_q, 1);
+        for (int i = 0; i < kRingTS; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 1); }
+        for (int t = 0; t < 2; ++t) {
+            mbar_init(bar_s_full + 8 * t, 1);
+            mbar_init(bar_p_full + 8 * t, 128);
+            mbar_init(bar_q_ready + 8 * t, 128);
+            mbar_init(bar_o_done + 8 * t, 1);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, kTmemCols);
+        tmem_relinquish();
+    }
+    for (int i = threadIdx.x; i < kTileBytes / 16; i += kAttnThreads)
+        *reinterpret_cast<uint4*>(gen + (sOnes - base) + i * 16) = make_uint4(0x3C003C00u, 0x3C003C00u, 0x3C003C00u, 0x3C003C00u);
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gen + (tmem_slot - base));
+
+    if (warp == 0) {
+        // ================================ TMA producer ================================
+        if (elect_one()) {
+            mbar_expect_tx(bar_q, 2 * kTileBytes);
+            tma_load_3d(sQ, &tm_qkv, bar_q, head * kD, q0, img);
+            tma_load_3d(sQ + kTileBytes, &tm_qkv, bar_q, head * kD, q0 + kQ, img);
+        }
+        __syncwarp();
+        for (int i = 0; i < 2 * nkv; ++i) {                     // item 2j = K_j, 2j+1 = V_j
+            const int st = i % kRingTS;
+            mbar_wait(bar_empty + 8 * st, ((uint32_t)(i / kRingTS) & 1u) ^ 1u);
+            if (elect_one()) {
+                mbar_expect_tx(bar_full + 8 * st, kTileBytes);
+                const int col = ((i & 1) ? 2 * C : C) + head * kD;
+                tma_load_3d(sRing + st * kTileBytes, &tm_qkv, bar_full + 8 * st, col, (i >> 1) * kKV, img);
+            }
+            __syncwarp();
+        }
+    } else if (warp == 1) {
+        // ================================ MMA issuer ================================
+        const uint32_t idesc_qk = make_idesc_f16(kKV, 0, 0);
+        const uint32_t idesc_pv = make_idesc_f16(kOCols, 0, 1);               // B (= [V | ones]) is MN-major, N = 80
+        auto issue_qk = [&](int t, int stage) {                              // S_t = Q_t[tmem] K^T[smem]
+            const uint64_t dk = make_desc_sw128(sRing + stage * kTileBytes);
+            if (elect_one()) {
+#pragma unroll
+                for (int kk = 0; kk < kD / 16; ++kk)
+                    umma_f16_ts(tmem_base + t * 128, tmem_base + kColQ + t * kColStride + 8 * kk, dk + 2 * kk, idesc_qk, kk > 0 ? 1u : 0u);
+                umma_commit(bar_s_full + 8 * t);
+            }
+            __syncwarp();
+        };
+        auto issue_pv = [&](int t, int stage, bool first, bool last) {      // O_t += P_t[tmem] [V | ones][smem]
+            const uint32_t v_addr = sRing + stage * kTileBytes;
+            const uint64_t dv = (uint64_t((v_addr & 0x3FFFF) >> 4)) | (uint64_t((sOnes - v_addr) >> 4) << 16) |
+                                (uint64_t(1024 >> 4) << 32) | (uint64_t(1) << 46) | (uint64_t(2) << 61);
+            if (elect_one()) {
+#pragma unroll
+                for (int kk = 0; kk < kKV / 16; ++kk)
+                    umma_f16_ts(tmem_base + kColO + t * kColStride, tmem_base + t * 128 + 8 * kk, dv + (uint64_t)kk * (2048 >> 4), idesc_pv,
+                                (!first || kk > 0) ? 1u : 0u);
+                if (last) umma_commit(bar_o_done + 8 * t);
+            }
+            __syncwarp();
+        };
+        mbar_wait(bar_q_ready + 0, 0);
+        mbar_wait(bar_q_ready + 8, 0);
+        mbar_wait(bar_full + 0, 0);                                           // K_0 in ring slot 0
+        tc_fence_after();
+        issue_qk(0, 0);
+        issue_qk(1, 0);
+        if (elect_one()) umma_commit(bar_empty + 0);
+        __syncwarp();
+        for (int j = 0; j < nkv; ++j) {
+            const bool more = (j + 1 < nkv);
+            const int ik = 2 * j + 2, iv = 2 * j + 1;
+            const int sk = ik % kRingTS, sv = iv % kRingTS;
+            mbar_wait(bar_full + 8 * sv, (uint32_t)(iv / kRingTS) & 1u);                  // V_j
+            if (more) mbar_wait(bar_full + 8 * sk, (uint32_t)(ik / kRingTS) & 1u);        // K_{j+1}
+            for (int t = 0; t < 2; ++t) {
+                mbar_wait(bar_p_full + 8 * t, (uint32_t)j & 1u);              // P_t(j) in TMEM, every read of S_t(j) done
+                tc_fence_after();
+                issue_pv(t, sv, j == 0, !more);
+                if (more) issue_qk(t, sk);                                    // in issue order behind PV(t, j): may overwrite S_t | P_t
+            }
+            if (elect_one()) {
+                if (more) umma_commit(bar_empty + 8 * sk);
+                umma_commit(bar_empty + 8 * sv);
+            }
+            __syncwarp();
+        }
+    } else {
+        // ================= softmax / correction / epilogue: one thread per query row of tile t =================
+        const int t = (warp - 2) >> 2;
+        const int qd = warp & 3;
+        const int row = qd * 32 + lane;
+        const uint32_t lane_sel = (uint32_t)(qd * 32) << 16;
+        const uint32_t tS = tmem_base + t * 128 + lane_sel, tO = tmem_base + kColO + t * kColStride + lane_sel;
+        const uint32_t sw = (uint32_t)row & 7u;
+        uint8_t* pQ = gen + (sQ - base) + t * kTileBytes + row * 128;      // this row of the Q tile (SW128), later of the O staging tile
+        // ---- Q row: TMA tile -> registers -> TMEM (A operand of every QK^T of this tile)
+        mbar_wait(bar_q, 0);
+        {
+            uint32_t r[32];
+#pragma unroll
+            for (int ch = 0; ch < 8; ++ch) {
+                const uint4 u = *reinterpret_cast<const uint4*>(pQ + (((uint32_t)ch ^ sw) << 4));
+                r[4 * ch] = u.x; r[4 * ch + 1] = u.y; r[4 * ch + 2] = u.z; r[4 * ch + 3] = u.w;
+            }
+            const uint32_t tQ = tmem_base + kColQ + t * kColStride + lane_sel;
+            tmem_st_32x32b_x16(tQ, r);
+            tmem_st_32x32b_x16(tQ + 16, r + 16);
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(bar_q_ready + 8 * t);
+        }
+        float m_ref = -INFINITY;
+        const float c = a.scale_log2;
+        for (int j = 0; j < nkv; ++j) {
+            const int valid = a.S - j * kKV;                       // keys beyond S are zero-filled by TMA: mask them
+            const bool masked = valid < kKV;
+            mbar_wait(bar_s_full + 8 * t, (uint32_t)j & 1u);       // S_t(j) ready; PV(t, j-1) retired (issue order): O_t is ours
+            tc_fence_after();
+            // pass 1: row max.  The TMEM load of chunk ch+1 is in flight while chunk ch is reduced.
+            float mx = -INFINITY;
+            if (!masked) {
+                uint32_t ra[32], rb[32];
+                tmem_ld_32x32b_x32(tS, ra);
+                tmem_ld_wait();
+                tmem_ld_32x32b_x32(tS + 32, rb);
+                mx = row_max_chunk(ra, mx);
+                tmem_ld_wait();
+                tmem_ld_32x32b_x32(tS + 64, ra);
+                mx = row_max_chunk(rb, mx);
+                tmem_ld_wait();
+                tmem_ld_32x32b_x32(tS + 96, rb);
+                mx = row_max_chunk(ra, mx);
+                tmem_ld_wait();
+                mx = row_max_chunk(rb, mx);
+            } else {                                             // ragged last KV tile (S % 128 != 0): simple rolled loop
+#pragma unroll 1
+                for (int ch = 0; ch < 4; ++ch) {
+                    uint32_t r[32];
+                    tmem_ld_32x32b_x32(tS + ch * 32, r);
+                    tmem_ld_wait();
+                    mask_chunk(r, ch * 32, valid);
+                    mx = row_max_chunk(r, mx);
+                }
+            }
+            float alpha = 1.f;
+            const bool grow = (mx - m_ref) * c > kRescaleThreshold;
+            const bool any_grow = __any_sync(0xffffffffu, grow) || (j == 0);
+            if (any_grow) {
+                const float m_new = fmaxf(m_ref, mx);
+                alpha = (m_ref == -INFINITY) ? 0.f : fast_exp2((m_ref - m_new) * c);
+                m_ref = m_new;
+                if (j > 0) {
+#pragma unroll
+                    for (int ch = 0; ch < kOCols / 16; ++ch) {      // 64 output columns + the row-sum columns
+                        uint32_t r[16];
+                        tmem_ld_32x32b_x16(tO + ch * 16, r);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) r[e] = __float_as_uint(__uint_as_float(r[e]) * alpha);
+                        tmem_st_32x32b_x16(tO + ch * 16, r);
+                    }
+                }
+            }
+            // pass 2: p = 2^((s - m_ref) * c), packed fp16, written over the first half of this row's own scores
+            const float mc = m_ref * c;
+            if (!masked) {
+                uint32_t ra[32], rb[32], p[16];
+                tmem_ld_32x32b_x32(tS, ra);
+                tmem_ld_wait();
+                tmem_ld_32x32b_x32(tS + 32, rb);
+                exp_pack<POLY>(ra, c, mc, p);
+                tmem_ld_wait();
+                tmem_st_32x32b_x16(tS, p);                       // P keys 0..31 -> columns [0,16): inside score chunk 0 (read)
+                tmem_ld_32x32b_x32(tS + 64, ra);
+                exp_pack<POLY>(rb, c, mc, p);
+                tmem_ld_wait();
+                tmem_st_32x32b_x16(tS + 16, p);                  // keys 32..63 -> [16,32)
+                tmem_ld_32x32b_x32(tS + 96, rb);
+                exp_pack<POLY>(ra, c, mc, p);
+                tmem_ld_wait();
+                tmem_st_32x32b_x16(tS + 32, p);                  // keys 64..95 -> [32,48): score chunk 1 was consumed two steps ago
+                exp_pack<POLY>(rb, c, mc, p);
+                tmem_st_32x32b_x16(tS + 48, p);                  // keys 96..127 -> [48,64)
+            } else {
+                uint32_t pk[64];
+#pragma unroll
+                for (int ch = 0; ch < 4; ++ch) {                 // every score chunk is read before any P word is stored
+                    uint32_t r[32];
+                    tmem_ld_32x32b_x32(tS + ch * 32, r);
+                    tmem_ld_wait();
+                    mask_chunk(r, ch * 32, valid);
+                    exp_pack<0>(r, c, mc, pk + 16 * ch);
+                }
+#pragma unroll
+                for (int ch = 0; ch < 4; ++ch) tmem_st_32x32b_x16(tS + 16 * ch, pk + 16 * ch);
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(bar_p_full + 8 * t);
+        }
+        // ---- epilogue: O / l -> fp16 -> smem (SW128, this tile's Q buffer) -> TMA store
+        mbar_wait(bar_o_done + 8 * t, 0);
+        tc_fence_after();
+        float inv;
+        {
+            uint32_t r[16];
+            tmem_ld_32x32b_x16(tO + 64, r);                      // row sum l = (P @ ones), fp32 from the tensor core
+            tmem_ld_wait();
+            inv = 1.f / __uint_as_float(r[0]);
+        }
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+            uint32_t r[16];
+            tmem_ld_32x32b_x16(tO + ch * 16, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int v8 = 0; v8 < 2; ++v8) {
+                uint4 u;
+                __half2* hh = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    hh[e] = __floats2half2_rn(__uint_as_float(r[v8 * 8 + 2 * e]) * inv, __uint_as_float(r[v8 * 8 + 2 * e + 1]) * inv);
+                const uint32_t chunk16 = (uint32_t)(ch * 2 + v8);
+                *reinterpret_cast<uint4*>(pQ + ((chunk16 ^ sw) << 4)) = u;
+            }
+        }
+        fence_proxy_async_smem();
+        if (t == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+        else        asm volatile("bar.sync 2, 128;" ::: "memory");
+        if (qd == 2 && lane == 0) {                              // first warp of each softmax group (warps 2 and 6)
+            asm volatile(
+                "cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
+                ::"l"(reinterpret_cast<uint64_t>(&tm_out)), "r"(sQ + t * kTileBytes), "r"(head * kD), "r"(q0 + t * kQ), "r"(img) : "memory");
+            tma_store_commit();
+            tma_store_wait_all<0>();
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        tc_fence_after();
+        tmem_dealloc(tmem_base, kTmemCols);
+    }
+}
+
+
+// =====================================================================================================================
+// TS-mode, TWO threads per query row (18 warps): the softmax of the 8-warp kernels is latency-bound -- ncu: every softmax
+// warp is busy 87 % of the time at 0.28 IPC (~790 dependent-ish instructions per KV tile), MUFU 55 %, issue slots 55 %,
+// with only two softmax warps per SM sub-partition to hide each other's latencies.  Here every row of tile t is owned by a
+// PRIMARY thread (warps 2-5 / 10-13) and a HELPER thread (warps 6-9 / 14-17) on the same TMEM lane:
+//   primary: pass 1 over all 128 scores (row max), reference-max update + lazy O rescale, publishes m_ref * c through
+//            shared memory, `bar.arrive`; then exponentials of keys 0..63 -> P columns [0,32)
+//   helper:  `bar.sync` on the same named barrier (so every primary has finished READING the scores of this KV tile),
+//            reads m_ref * c, exponentials of keys 64..127 -> P columns [64,96) (aliased inside its own half of S_t)
+// Four softmax warps per sub-partition, ~370 / ~300 instructions per KV tile each.  P_t is therefore two 32-column pieces
+// (k-steps 0..3 at column 8 kk, k-steps 4..7 at column 64 + 8 (kk - 4)); everything else is as in attn_spatial_ts_kernel.
+constexpr int kAttnThreads2 = 18 * 32;
+constexpr int kAttnSmemTS2 = kAttnSmemTS + 1024;                            // + m_ref * c hand-off [2 tiles][128 rows] fp32
+
+template <int POLY>
+__global__ void __launch_bounds__(kAttnThreads2, 1)
+attn_spatial_ts2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_out,
+                        const __grid_constant__ AttnArgs a, int C) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t sQ = base;                                    // 2 tiles; reused as the O staging tiles of the epilogue
+    const uint32_t sRing = sQ + 2 * kTileBytes;
+    const uint32_t sOnes = sRing + kRingTS * kTileBytes;
+    const uint32_t sMref = sOnes + kTileBytes;                   // float [2][128]
+    const uint32_t bars = sMref + 1024;
+    const uint32_t bar_q = bars;
+    const uint32_t bar_full = bars + 8;                          // [kRingTS]
+    const uint32_t bar_empty = bar_full + 8 * kRingTS;           // [kRingTS]
+    const uint32_t bar_s_full = bar_empty + 8 * kRingTS;         // [2]
+    const uint32_t bar_p_full = bar_s_full + 16;                 // [2]  256 arrivals: primary + helper threads
+    const uint32_t bar_q_ready = bar_p_full + 16;                // [2]  256 arrivals
+    const uint32_t bar_o_done = bar_q_ready + 16;                // [2]
+    const uint32_t tmem_slot = bar_o_done + 16;
+    uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q0 = blockIdx.x * 2 * kQ, head = blockIdx.y, img = blockIdx.z;
+    const int nkv = a.nkv;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tm_qkv);
+        tma_prefetch_desc(&tm_out);
+        mbar_init(bar_q, 1);
+        for (int i = 0; i < kRingTS; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 1); }
+        for (int t = 0; t < 2; ++t) {
+            mbar_init(bar_s_full + 8 * t, 1);
+            mbar_init(bar_p_full + 8 * t, 256);
+            mbar_init(bar_q_ready + 8 * t, 256);
+            mbar_init(bar_o_done + 8 * t, 1);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, kTmemCols);
+        tmem_relinquish();
+    }
+    for (int i = threadIdx.x; i < kTileBytes / 16; i += kAttnThreads2)
+        *reinterpret_cast<uint4*>(gen + (sOnes - base) + i * 16) = make_uint4(0x3C003C00u, 0x3C003C00u, 0x3C003C00u, 0x3C003C00u);
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gen + (tmem_slot - base));
+
+    if (warp == 0) {
+        // ================================ TMA producer ================================
+        if (elect_one()) {
+            mbar_expect_tx(bar_q, 2 * kTileBytes);
+            tma_load_3d(sQ, &tm_qkv, bar_q, head * kD, q0, img);
+            tma_load_3d(sQ + kTileBytes, &tm_qkv, bar_q, head * kD, q0 + kQ, img);
+        }
+        __syncwarp();
+        for (int i = 0; i < 2 * nkv; ++i) {                     // item 2j = K_j, 2j+1 = V_j
+            const int st = i % kRingTS;
+            mbar_wait(bar_empty + 8 * st, ((uint32_t)(i / kRingTS) & 1u) ^ 1u);
+            if (elect_one()) {
+                mbar_expect_tx(bar_full + 8 * st, kTileBytes);
+                const int col = ((i & 1) ? 2 * C : C) + head * kD;
+                tma_load_3d(sRing + st * kTileBytes, &tm_qkv, bar_full + 8 * st, col, (i >> 1) * kKV, img);
+            }
+            __syncwarp();
+        }
+    } else if (warp == 1) {
+        // ================================ MMA issuer ================================
+        const uint32_t idesc_qk = make_idesc_f16(kKV, 0, 0);
+        const uint32_t idesc_pv = make_idesc_f16(kOCols, 0, 1);               // B (= [V | ones]) is MN-major, N = 80
+        auto issue_qk = [&](int t, int stage) {                              // S_t = Q_t[tmem] K^T[smem]
+            const uint64_t dk = make_desc_sw128(sRing + stage * kTileBytes);
+            if (elect_one()) {
+#pragma unroll
+                for (int kk = 0; kk < kD / 16; ++kk)
+                    umma_f16_ts(tmem_base + t * 128, tmem_base + kColQ + t * kColStride + 8 * kk, dk + 2 * kk, idesc_qk, kk > 0 ? 1u : 0u);
+                umma_commit(bar_s_full + 8 * t);
+            }
+            __syncwarp();
+        };
+        auto issue_pv = [&](int t, int stage, bool first, bool last) {      // O_t += P_t[tmem] [V | ones][smem]
+            const uint32_t v_addr = sRing + stage * kTileBytes;
+            const uint64_t dv = (uint64_t((v_addr & 0x3FFFF) >> 4)) | (uint64_t((sOnes - v_addr) >> 4) << 16) |
+                                (uint64_t(1024 >> 4) << 32) | (uint64_t(1) << 46) | (uint64_t(2) << 61);
+            if (elect_one()) {
+#pragma unroll
+                for (int kk = 0; kk < kKV / 16; ++kk)           // keys 0..63 in P columns [0,32), keys 64..127 in [64,96)
+                    umma_f16_ts(tmem_base + kColO + t * kColStride, tmem_base + t * 128 + (kk >> 2) * 64 + 8 * (kk & 3),
+                                dv + (uint64_t)kk * (2048 >> 4), idesc_pv, (!first || kk > 0) ? 1u : 0u);
+                if (last) umma_commit(bar_o_done + 8 * t);
+            }
+            __syncwarp();
+        };
+        mbar_wait(bar_q_ready + 0, 0);
+        mbar_wait(bar_q_ready + 8, 0);
+        mbar_wait(bar_full + 0, 0);                                           // K_0 in ring slot 0
+        tc_fence_after();
+        issue_qk(0, 0);
+        issue_qk(1, 0);
+        if (elect_one()) umma_commit(bar_empty + 0);
+        __syncwarp();
+        for (int j = 0; j < nkv; ++j) {
+            const bool more = (j + 1 < nkv);
+            const int ik = 2 * j + 2, iv = 2 * j + 1;
+            const int sk = ik % kRingTS, sv = iv % kRingTS;
+            mbar_wait(bar_full + 8 * sv, (uint32_t)(iv / kRingTS) & 1u);                  // V_j
+            if (more) mbar_wait(bar_full + 8 * sk, (uint32_t)(ik / kRingTS) & 1u);        // K_{j+1}
+            for (int t = 0; t < 2; ++t) {
+                mbar_wait(bar_p_full + 8 * t, (uint32_t)j & 1u);
+                tc_fence_after();
+                issue_pv(t, sv, j == 0, !more);
+                if (more) issue_qk(t, sk);
+            }
+            if (elect_one()) {
+                if (more) umma_commit(bar_empty + 8 * sk);
+                umma_commit(bar_empty + 8 * sv);
+            }
+            __syncwarp();
+        }
+    } else {
+        // ================= softmax: tile t, primary (hf = 0) / helper (hf = 1) thread of one query row =================
+        const int sidx = warp - 2;
+        const int t = sidx >> 3;
+        const int hf = (sidx >> 2) & 1;
+        const int qd = warp & 3;
+        const int row = qd * 32 + lane;
+        const uint32_t lane_sel = (uint32_t)(qd * 32) << 16;
+        const uint32_t tS = tmem_base + t * 128 + lane_sel, tO = tmem_base + kColO + t * kColStride + lane_sel;
+        const uint32_t tSh = tS + hf * 64;                                   // this thread's 64 scores; its P words go to [tSh, tSh + 32)
+        const uint32_t sw = (uint32_t)row & 7u;
+        uint8_t* pQ = gen + (sQ - base) + t * kTileBytes + row * 128;
+        volatile float* mref = reinterpret_cast<volatile float*>(gen + (sMref - base)) + t * 128 + row;
+        // named barrier 1 + t: the 128 primaries arrive, the 128 helpers sync
+        // ---- Q row: TMA tile -> registers -> TMEM; each of the two threads copies half of the row (32 halves = 16 columns)
+        mbar_wait(bar_q, 0);
+        {
+            uint32_t r[16];
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch) {
+                const uint4 u = *reinterpret_cast<const uint4*>(pQ + (((uint32_t)(hf * 4 + ch) ^ sw) << 4));
+                r[4 * ch] = u.x; r[4 * ch + 1] = u.y; r[4 * ch + 2] = u.z; r[4 * ch + 3] = u.w;
+            }
+            tmem_st_32x32b_x16(tmem_base + kColQ + t * kColStride + hf * 16 + lane_sel, r);
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(bar_q_ready + 8 * t);
+        }
+        float m_ref = -INFINITY;
+        const float c = a.scale_log2;
+        for (int j = 0; j < nkv; ++j) {
+            const int valid = a.S - j * kKV;
+            const bool masked = valid < kKV;
+            float mc;
+            if (hf == 0) {
+                mbar_wait(bar_s_full + 8 * t, (uint32_t)j & 1u);   // S_t(j) ready; PV(t, j-1) retired: O_t is ours
+                tc_fence_after();
+                float mx = -INFINITY;
+                if (!masked) {
+                    uint32_t ra[32], rb[32];
+                    tmem_ld_32x32b_x32(tS, ra);
+                    tmem_ld_wait();
+                    tmem_ld_32x32b_x32(tS + 32, rb);
+                    mx = row_max_chunk(ra, mx);
+                    tmem_ld_wait();
+                    tmem_ld_32x32b_x32(tS + 64, ra);
+                    mx = row_max_chunk(rb, mx);
+                    tmem_ld_wait();
+                    tmem_ld_32x32b_x32(tS + 96, rb);
+                    mx = row_max_chunk(ra, mx);
+                    tmem_ld_wait();
+                    mx = row_max_chunk(rb, mx);
+                } else {
+#pragma unroll 1
+                    for (int ch = 0; ch < 4; ++ch) {
+                        uint32_t r[32];
+                        tmem_ld_32x32b_x32(tS + ch * 32, r);
+                        tmem_ld_wait();
+                        mask_chunk(r, ch * 32, valid);
+                        mx = row_max_chunk(r, mx);
+                    }
+                }
+                const bool grow = (mx - m_ref) * c > kRescaleThreshold;
+                const bool any_grow = __any_sync(0xffffffffu, grow) || (j == 0);
+                float alpha = 1.f;
+                if (any_grow) {
+                    const float m_new = fmaxf(m_ref, mx);
+                    alpha = (m_ref == -INFINITY) ? 0.f : fast_exp2((m_ref - m_new) * c);
+                    m_ref = m_new;
+                }
+                mc = m_ref * c;
+                *mref = mc;                                      // hand-off to the helper thread of this row
+                tc_fence_before();                               // the helper's tcgen05 accesses are ordered after what this thread observed
+                if (t == 0) asm volatile("bar.arrive 1, 256;" ::: "memory");
+                else        asm volatile("bar.arrive 2, 256;" ::: "memory");
+                if (any_grow && j > 0) {
+#pragma unroll
+                    for (int ch = 0; ch < kOCols / 16; ++ch) {
+                        uint32_t r[16];
+                        tmem_ld_32x32b_x16(tO + ch * 16, r);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) r[e] = __float_as_uint(__uint_as_float(r[e]) * alpha);
+                        tmem_st_32x32b_x16(tO + ch * 16, r);
+                    }
+                }
+            } else {
+                // every primary of this tile has read the scores of KV tile j (and published its reference max)
+                if (t == 0) asm volatile("bar.sync 1, 256;" ::: "memory");
+                else        asm volatile("bar.sync 2, 256;" ::: "memory");
+                tc_fence_after();
+                mc = *mref;
+            }
+            // exponentials of this thread's 64 keys -> 32 packed words over the first half of its own score columns
+            {
+                uint32_t ra[32], rb[32], p[16];
+                tmem_ld_32x32b_x32(tSh, ra);
+                tmem_ld_wait();
+                tmem_ld_32x32b_x32(tSh + 32, rb);
+                if (masked) mask_chunk(ra, hf * 64, valid);
+                exp_pack<POLY>(ra, c, mc, p);
+                tmem_ld_wait();
+                tmem_st_32x32b_x16(tSh, p);
+                if (masked) mask_chunk(rb, hf * 64 + 32, valid);
+                exp_pack<POLY>(rb, c, mc, p);
+                tmem_st_32x32b_x16(tSh + 16, p);
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(bar_p_full + 8 * t);
+        }
+        // ---- epilogue: O / l -> fp16 -> smem (SW128, this tile's Q buffer) -> TMA store; each thread converts 32 columns
+        mbar_wait(bar_o_done + 8 * t, 0);
+        tc_fence_after();
+        float inv;
+        {
+            uint32_t r[16];
+            tmem_ld_32x32b_x16(tO + 64, r);
+            tmem_ld_wait();
+            inv = 1.f / __uint_as_float(r[0]);
+        }
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch) {
+            uint32_t r[16];
+            tmem_ld_32x32b_x16(tO + (hf * 2 + ch) * 16, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int v8 = 0; v8 < 2; ++v8) {
+                uint4 u;
+                __half2* hh = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    hh[e] = __floats2half2_rn(__uint_as_float(r[v8 * 8 + 2 * e]) * inv, __uint_as_float(r[v8 * 8 + 2 * e + 1]) * inv);
+                const uint32_t chunk16 = (uint32_t)((hf * 2 + ch) * 2 + v8);
+                *reinterpret_cast<uint4*>(pQ + ((chunk16 ^ sw) << 4)) = u;
+            }
+        }
+        fence_proxy_async_smem();
+        if (t == 0) asm volatile("bar.sync 3, 256;" ::: "memory");
+        else        asm volatile("bar.sync 4, 256;" ::: "memory");
+        if (hf == 0 && qd == 2 && lane == 0) {                    // warps 2 and 10
+            asm volatile(
+                "cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
+                ::"l"(reinterpret_cast<uint64_t>(&tm_out)), "r"(sQ + t * kTileBytes), "r"(head * kD), "r"(q0 + t * kQ), "r"(img) : "memory");
+            tma_store_commit();
+            tma_store_wait_all<0>();
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        tc_fence_after();
+        tmem_dealloc(tmem_base, kTmemCols);
+    }
+}
+
 }  // namespace wiw
 
 using namespace wiw;
@@ -402,18 +1010,22 @@ extern "C" int wiw_attention_spatial(const void* qkv, void* out, int images, int
     a.scale_log2 = 0.125f * 1.4426950408889634f;
     static unsigned long long attr_set = 0;
     if (first_call_on_device(&attr_set)) {
-        WIW_CHECK_CUDA(cudaFuncSetAttribute(attn_spatial_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
         WIW_CHECK_CUDA(cudaFuncSetAttribute(attn_spatial_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
-        WIW_CHECK_CUDA(cudaFuncSetAttribute(attn_spatial_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
+        WIW_CHECK_CUDA(cudaFuncSetAttribute(attn_spatial_ts_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemTS));
+        WIW_CHECK_CUDA(cudaFuncSetAttribute(attn_spatial_ts_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemTS));
+        WIW_CHECK_CUDA(cudaFuncSetAttribute(attn_spatial_ts2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemTS2));
+        WIW_CHECK_CUDA(cudaFuncSetAttribute(attn_spatial_ts2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemTS2));
     }
-    // share of the exponentials evaluated on the FMA pipe instead of MUFU (development aid for A/B runs; see exp2_poly)
-    static const int poly = getenv("WIW_ATTN_POLY") ? atoi(getenv("WIW_ATTN_POLY")) : 1;       // A/B on B200: 1 of 4 pairs on the FMA pipe = +6 % at S=9216; 2 of 4 = -4 %
+    // development switches for same-box A/B runs: WIW_ATTN_TS=0 -> the shared-memory-operand kernel; WIW_ATTN_POLY = exponential
+    // pairs (of every 4) evaluated on the FMA pipe instead of MUFU (see exp2_poly)
+    static const int ts = getenv("WIW_ATTN_TS") ? atoi(getenv("WIW_ATTN_TS")) : 2;        // 0 = SS kernel, 1 = TS 8 softmax warps, 2 = TS 16
+    static const int poly = getenv("WIW_ATTN_POLY") ? atoi(getenv("WIW_ATTN_POLY")) : 1;
     dim3 grid((S + 2 * kQ - 1) / (2 * kQ), C / 64, images);
-    // (a single-pass softmax variant -- one TMEM sweep per KV tile, probabilities parked in registers -- gave the same results
-    // 3.5 % slower on B200 and was removed again: DESIGN.md section 4, profiles/r01_perf_attn_onepass_ab_v9.txt)
-    if (poly == 1) attn_spatial_kernel<1><<<grid, kAttnThreads, kAttnSmem, stream>>>(tm_qkv, tm_out, a, C);
-    else if (poly == 2) attn_spatial_kernel<2><<<grid, kAttnThreads, kAttnSmem, stream>>>(tm_qkv, tm_out, a, C);
-    else attn_spatial_kernel<0><<<grid, kAttnThreads, kAttnSmem, stream>>>(tm_qkv, tm_out, a, C);
+    if (!ts) attn_spatial_kernel<1><<<grid, kAttnThreads, kAttnSmem, stream>>>(tm_qkv, tm_out, a, C);
+    else if (ts == 2 && poly == 2) attn_spatial_ts2_kernel<2><<<grid, kAttnThreads2, kAttnSmemTS2, stream>>>(tm_qkv, tm_out, a, C);
+    else if (ts == 2) attn_spatial_ts2_kernel<1><<<grid, kAttnThreads2, kAttnSmemTS2, stream>>>(tm_qkv, tm_out, a, C);
+    else if (poly == 2) attn_spatial_ts_kernel<2><<<grid, kAttnThreads, kAttnSmemTS, stream>>>(tm_qkv, tm_out, a, C);
+    else attn_spatial_ts_kernel<1><<<grid, kAttnThreads, kAttnSmemTS, stream>>>(tm_qkv, tm_out, a, C);
     WIW_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

@@ -303,7 +303,7 @@ class WorldModelWorker:
                 b_image = np.stack([np.asarray(Image.open(os.path.join(d, "cond_rgb.png")).convert("RGB")).transpose(2, 0, 1)
                                     for d in save_dirs])
         except (OSError, ValueError) as e:
-            raise RequestDataError(f"cannot read the request's observation / actions: {e!r}") from e
+            raise RequestDataError(f"cannot read the request's observation / actions: {type(e).__name__}: {e}") from e
         if b_image.ndim != 4 or b_image.dtype != np.uint8 or b_image.shape[1] not in (3, 4):
             raise RequestDataError(f"b_image should be uint8 B C H W with 3 or 4 channels, got {b_image.dtype} {b_image.shape}")
         if b_action.ndim != 2 or len(b_action) != len(save_dirs) or len(b_image) != len(save_dirs):
