@@ -27,7 +27,7 @@ __device__ __forceinline__ void umma_ts_2sm(uint32_t tmem_d, uint32_t tmem_a, ui
         ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
 }
 
-template <int CG, int M, int N, int TS, int NACC>
+template <int CG, int M, int N, int TS, int NACC, int BMN = 0>
 __global__ void __launch_bounds__(128, 1) mma_bench(int outer, long long* out) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -45,7 +45,7 @@ __global__ void __launch_bounds__(128, 1) mma_bench(int outer, long long* out) {
     const uint32_t tmem = *slot_ptr;
     const int rank = (CG == 2) ? (int)cluster_ctarank() : 0;
     if (threadIdx.x < 32 && rank == 0) {
-        constexpr uint32_t idesc = make_idesc_f16(N, 0, 0, M);
+        constexpr uint32_t idesc = make_idesc_f16(N, 0, BMN, M);
         // accumulators: NACC x N columns from column 0; the TMEM A operand (64 columns = K 128) sits above them
         constexpr uint32_t a_col = (NACC * N <= 448) ? 448 : 0;
         static_assert(NACC * N <= 512, "accumulators do not fit");
@@ -61,7 +61,12 @@ __global__ void __launch_bounds__(128, 1) mma_bench(int outer, long long* out) {
                     for (int i = 0; i < kUnroll; ++i) {
                         const uint32_t st = (i >> 2) & (kStages - 1), kk = i & 3;
                         const uint64_t da = make_desc_sw128(base + st * kStage) + 2 * kk;
-                        const uint64_t db = make_desc_sw128(base + st * kStage + kStageA) + 2 * kk;
+                        // BMN: B consumed MN-major from a [k rows][64 elements] SW128 tile (the attention's V operand): K groups of 8 rows at
+                        // SBO = 1024 B, the second 64-wide N atom (N = 80: the tile of ones) at LBO = 16 KB; a K = 16 step advances 2048 B
+                        const uint32_t b_addr = base + st * kStage + kStageA;
+                        const uint64_t db = BMN ? ((uint64_t((b_addr & 0x3FFFF) >> 4)) | (uint64_t(16384 >> 4) << 16) | (uint64_t(1024 >> 4) << 32) |
+                                                   (uint64_t(1) << 46) | (uint64_t(2) << 61)) + (uint64_t)kk * (2048 >> 4)
+                                                : make_desc_sw128(b_addr) + 2 * kk;
                         const uint32_t d = tmem + (uint32_t)((i % NACC) * N);
                         if (CG == 2) { if (TS) umma_ts_2sm(d, tmem + a_col + 8 * kk, db, idesc, 1u); else umma_f16_ss_2sm(d, da, db, idesc, 1u); }
                         else { if (TS) umma_f16_ts(d, tmem + a_col + 8 * kk, db, idesc, 1u); else umma_f16_ss(d, da, db, idesc, 1u); }
@@ -90,11 +95,11 @@ __global__ void __launch_bounds__(128, 1) mma_bench(int outer, long long* out) {
 
 static long long* g_out = nullptr;
 
-template <int CG, int M, int N, int TS, int NACC>
+template <int CG, int M, int N, int TS, int NACC, int BMN = 0>
 static int run() {
     if (!g_out) cudaMalloc(&g_out, 32);
     const int smem = 1024 + kStages * kStage + 64, outer = 32, grid = 148;
-    auto k = mma_bench<CG, M, N, TS, NACC>;
+    auto k = mma_bench<CG, M, N, TS, NACC, BMN>;
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (CG == 1) {
         k<<<grid, 128, smem>>>(outer, g_out);
@@ -112,9 +117,9 @@ static int run() {
     const double n = double(outer) * kUnroll;
     // per-SM operand bytes one instruction reads from shared memory: A (M/CG rows x 16 x 2 B, unless TS) + B (N/CG rows x 32 B)
     const double smem_bytes = (TS ? 0.0 : (M / CG) * 32.0) + (N / CG) * 32.0;
-    printf("cg=%d %s M=%3d N=%3d acc=%d : done %6.1f  issue %6.1f cycles/MMA (%.2f GHz) | tensor floor M*N/(256*cg) = %5.1f | smem operand bytes/64 = %5.1f  %s\n",
-           CG, TS ? "TS" : "SS", M, N, NACC, double(h[0]) / n, double(h[1]) / n, double(h[0]) / double(h[2]),
-           double(M) * N / (256.0 * CG), smem_bytes / 64.0, e ? cudaGetErrorString(e) : "");
+    printf("cg=%d %s%s M=%3d N=%3d acc=%d : done %6.1f  issue %6.1f cycles/MMA (%.2f GHz) | tensor floor M*N/(256*cg) = %5.1f | smem operand bytes/128 = %5.1f  %s\n",
+           CG, TS ? "TS" : "SS", BMN ? " B=MN-major" : "", M, N, NACC, double(h[0]) / n, double(h[1]) / n, double(h[0]) / double(h[2]),
+           double(M) * N / (256.0 * CG), smem_bytes / 128.0, e ? cudaGetErrorString(e) : "");
     return e ? 1 : 0;
 }
 
@@ -181,6 +186,9 @@ int main() {
     bad |= run<2, 256, 64, 0, 4>();  bad |= run<2, 256, 128, 0, 2>(); bad |= run<2, 256, 160, 0, 2>(); bad |= run<2, 256, 224, 0, 2>();
     bad |= run<2, 256, 256, 0, 1>(); bad |= run<2, 256, 256, 0, 2>(); bad |= run<2, 128, 128, 0, 2>(); bad |= run<2, 128, 256, 0, 2>();
     bad |= run<2, 256, 128, 1, 2>(); bad |= run<2, 256, 256, 1, 1>();
+    // B consumed MN-major (the attention's P V product: V tile as loaded by TMA, N = 64 / 80)
+    bad |= run<1, 128, 64, 0, 4, 1>(); bad |= run<1, 128, 80, 0, 4, 1>(); bad |= run<1, 128, 64, 1, 4, 1>(); bad |= run<1, 128, 80, 1, 4, 1>();
+    bad |= run<1, 128, 128, 1, 2, 1>();
     for (int w : {1, 4, 8, 16}) run_tmem(0, w);
     for (int w : {1, 4, 8, 16}) run_tmem(1, w);
     return bad;

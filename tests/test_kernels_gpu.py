@@ -180,3 +180,16 @@ def test_gpu_resize_is_pil_exact(H, W, oh, ow):
     out2 = GpuResizer(H, W, oh, ow, DEV, requant=True)(torch.from_numpy(planes).to(DEV)).cpu().numpy()
     f = out.astype(np.float32) / np.float32(255)
     assert np.array_equal(out2, (np.clip(f, 0, 1) * 255).astype(np.uint8))
+
+
+@pytest.mark.parametrize("H,W,oh,ow", [(480, 480, 576, 1024), (384, 384, 576, 1024), (40, 48, 64, 128)])
+def test_gpu_resize_lanczos_is_pil_exact(H, W, oh, ow):
+    """The request side: the same integer resampler with Pillow's LANCZOS window == PIL Image.resize(LANCZOS) byte for byte
+    (video_processor.preprocess of a solver-sized observation, DP/image_processor.py:501)."""
+    from PIL import Image
+    from wiw_b200.resize import GpuResizer
+    planes = np.random.default_rng(H * 3 + W).integers(0, 256, size=(2, 3, H, W), dtype=np.uint8)
+    out = GpuResizer(H, W, oh, ow, DEV, requant=False, filt="lanczos")(torch.from_numpy(planes).to(DEV)).cpu().numpy()
+    for i in range(2):
+        ref = np.asarray(Image.fromarray(planes[i].transpose(1, 2, 0)).resize((ow, oh), Image.LANCZOS)).transpose(2, 0, 1)
+        assert np.array_equal(out[i], ref)

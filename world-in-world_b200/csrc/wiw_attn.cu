@@ -60,7 +60,14 @@ __device__ __forceinline__ float exp2_poly(float x) {
 struct AttnArgs {
     int S, nkv;
     float scale_log2;                            // (1/sqrt(d)) * log2(e)
+    long long* trace;                            // development aid (wiw_debug_attn_trace): clock64 stamps of CTA 0, else null
 };
+constexpr int kTraceIters = 8, kTraceFirst = 16, kTraceSlots = 16;      // stamps of KV tiles [16, 24): [iter][slot]
+__device__ __forceinline__ void trace_stamp(const AttnArgs& a, int j, int slot) {
+    if (a.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && j >= kTraceFirst && j < kTraceFirst + kTraceIters &&
+        (threadIdx.x & 31) == 0)
+        a.trace[(j - kTraceFirst) * kTraceSlots + slot] = clock64();
+}
 
 // keys at or beyond `valid` (zero-filled by TMA past the image's S rows) -> -inf before max / exp
 __device__ __forceinline__ void mask_chunk(uint32_t* r, int base, int valid) {
@@ -816,9 +823,11 @@ attn_spatial_ts2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
             if (more) mbar_wait(bar_full + 8 * sk, (uint32_t)(ik / kRingTS) & 1u);        // K_{j+1}
             for (int t = 0; t < 2; ++t) {
                 mbar_wait(bar_p_full + 8 * t, (uint32_t)j & 1u);
+                trace_stamp(a, j, 0 + 2 * t);                     // slots 0 / 2: P_t(j) seen by the MMA warp
                 tc_fence_after();
                 issue_pv(t, sv, j == 0, !more);
                 if (more) issue_qk(t, sk);
+                trace_stamp(a, j, 1 + 2 * t);                     // slots 1 / 3: PV(t, j) + QK(t, j+1) issued
             }
             if (elect_one()) {
                 if (more) umma_commit(bar_empty + 8 * sk);
@@ -862,6 +871,7 @@ attn_spatial_ts2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
             float mc;
             if (hf == 0) {
                 mbar_wait(bar_s_full + 8 * t, (uint32_t)j & 1u);   // S_t(j) ready; PV(t, j-1) retired: O_t is ours
+                if (qd == 2) trace_stamp(a, j, 4 + 4 * t);        // slots 4 / 8: S_t(j) seen by the primary warp of quadrant 2
                 tc_fence_after();
                 float mx = -INFINITY;
                 if (!masked) {
@@ -901,6 +911,7 @@ attn_spatial_ts2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
                 tc_fence_before();                               // the helper's tcgen05 accesses are ordered after what this thread observed
                 if (t == 0) asm volatile("bar.arrive 1, 256;" ::: "memory");
                 else        asm volatile("bar.arrive 2, 256;" ::: "memory");
+                if (qd == 2) trace_stamp(a, j, 5 + 4 * t);        // slots 5 / 9: pass 1 done, reference max published
                 if (any_grow && j > 0) {
 #pragma unroll
                     for (int ch = 0; ch < kOCols / 16; ++ch) {
@@ -918,6 +929,7 @@ attn_spatial_ts2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
                 else        asm volatile("bar.sync 2, 256;" ::: "memory");
                 tc_fence_after();
                 mc = *mref;
+                if (qd == 2) trace_stamp(a, j, 6 + 4 * t);        // slots 6 / 10: helper released
             }
             // exponentials of this thread's 64 keys -> 32 packed words over the first half of its own score columns
             {
@@ -936,6 +948,7 @@ attn_spatial_ts2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
             tmem_st_wait();
             tc_fence_before();
             mbar_arrive(bar_p_full + 8 * t);
+            if (qd == 2) trace_stamp(a, j, hf ? 12 + t : 7 + 4 * t);   // slots 7 / 11: primary's P written; 12 / 13: helper's
         }
         // ---- epilogue: O / l -> fp16 -> smem (SW128, this tile's Q buffer) -> TMA store; each thread converts 32 columns
         mbar_wait(bar_o_done + 8 * t, 0);
@@ -987,6 +1000,22 @@ attn_spatial_ts2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
 
 using namespace wiw;
 
+// development aid: wiw_debug_attn_trace(1) allocates a device buffer and makes the next launches stamp CTA 0's pipeline events
+// into it; wiw_debug_attn_trace(0) copies the stamps out (host buffer of kTraceIters * kTraceSlots int64) -- see scripts/attn_trace.py
+static long long* g_attn_trace = nullptr;
+extern "C" int wiw_debug_attn_trace(int enable, long long* host_out) {
+    if (enable) {
+        if (!g_attn_trace) WIW_CHECK_CUDA(cudaMalloc(&g_attn_trace, sizeof(long long) * kTraceIters * kTraceSlots));
+        WIW_CHECK_CUDA(cudaMemset(g_attn_trace, 0, sizeof(long long) * kTraceIters * kTraceSlots));
+        return 0;
+    }
+    if (!g_attn_trace || !host_out) return 1;
+    WIW_CHECK_CUDA(cudaMemcpy(host_out, g_attn_trace, sizeof(long long) * kTraceIters * kTraceSlots, cudaMemcpyDeviceToHost));
+    WIW_CHECK_CUDA(cudaFree(g_attn_trace));
+    g_attn_trace = nullptr;
+    return 0;
+}
+
 extern "C" int wiw_attention_spatial(const void* qkv, void* out, int images, int S, int C, wiw_stream_t stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     WIW_REQUIRE(qkv && out, "null pointer");
@@ -1008,6 +1037,7 @@ extern "C" int wiw_attention_spatial(const void* qkv, void* out, int images, int
     a.S = S;
     a.nkv = (S + kKV - 1) / kKV;
     a.scale_log2 = 0.125f * 1.4426950408889634f;
+    a.trace = g_attn_trace;
     static unsigned long long attr_set = 0;
     if (first_call_on_device(&attr_set)) {
         WIW_CHECK_CUDA(cudaFuncSetAttribute(attn_spatial_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));

@@ -57,8 +57,11 @@ CLIP_STD = (0.26862954, 0.26130258, 0.27577711)
 
 
 @torch.no_grad()
-def encode_image_clip(image01: torch.Tensor, image_encoder, dtype=torch.float16) -> torch.Tensor:
-    """pipeline :183-229.  image01 float [B,3,H,W] in [0,1] on the encoder's device -> [B, 1, D] (cond rows only)."""
+def encode_image_clip(image01: torch.Tensor, image_encoder, dtype=None) -> torch.Tensor:
+    """pipeline :183-229.  image01 float [B,3,H,W] in [0,1] on the encoder's device -> [B, 1, D] (cond rows only).
+    The CLIP input is cast to the encoder's own parameter dtype (pipeline :190, :214)."""
+    if dtype is None:
+        dtype = next(image_encoder.parameters()).dtype
     x = resize_with_antialiasing(image01 * 2.0 - 1.0, (224, 224))
     x = (x + 1.0) / 2.0
     mean = torch.tensor(CLIP_MEAN, device=x.device, dtype=x.dtype).view(1, 3, 1, 1)

@@ -213,6 +213,37 @@ class Navigator:
         self.noise_aug_strength = 0.02
 
     @torch.no_grad()
+    def encode_observation(self, images_u8: np.ndarray, gens=None):
+        """Conditioning of one request (pipeline :501-535): uint8 observations [b, 3|4, Hin, Win] of ANY size ->
+        (CLIP image embedding [b, 1, D], VAE latents of the noise-augmented frame fp16 [b, 4, H/8, W/8]).
+        The reference feeds the observation AS SENT (384x384 / 480x480 from the solvers) to _encode_image, whose antialiased
+        resize goes straight to 224x224 (pipeline :192-200), and separately resizes the PIL image to (W, H) with LANCZOS in
+        uint8 for the VAE branch (video_processor.preprocess, DP/image_processor.py:501; pipeline :520).
+        gens: one torch.Generator per branch (sharded serving) or None for the worker's persistent generator."""
+        from . import frontend
+        dev = self.device
+        H, W = self.image_height, self.image_width
+        obs = torch.from_numpy(np.ascontiguousarray(images_u8[:, :3])).to(dev)               # uint8 [b, 3, Hin, Win]
+        emb = frontend.encode_image_clip(obs.float() / 255.0, self.image_encoder)             # pil_to_numpy/numpy_to_pt: [0,1]; [b, 1, D]
+        if tuple(obs.shape[-2:]) != (H, W):
+            key = (int(obs.shape[-2]), int(obs.shape[-1]), H, W)
+            if getattr(self, "_obs_resizer_key", None) != key:
+                from .resize import GpuResizer
+                self._obs_resizer, self._obs_resizer_key = GpuResizer(*key, device=dev, requant=False, filt="lanczos"), key
+            obs = self._obs_resizer(obs)
+        pre = (obs.float() / 255.0) * 2.0 - 1.0                                              # video_processor.preprocess: normalize
+        if gens is not None:
+            # sharded serving: one generator state per branch, so a branch's noise does not depend on which rank rolls it out
+            noise = torch.stack([torch.randn(pre.shape[1:], generator=g, device=dev, dtype=pre.dtype) for g in gens])
+        else:
+            noise = torch.randn(pre.shape, generator=self.generator, device=dev, dtype=pre.dtype)   # pipeline :521-523
+        if self.vae_enc is not None:
+            image_latents = self.vae_enc.encode_mode(pre + self.noise_aug_strength * noise)
+        else:
+            image_latents = frontend.vae_encode_mode(self.vae_encoder_sd, pre + self.noise_aug_strength * noise).to(torch.float16)
+        return emb, image_latents
+
+    @torch.no_grad()
     def inference(self, actions: torch.Tensor, images_u8: np.ndarray, out_width=None, out_height=None,
                   latents: Optional[torch.Tensor] = None, on_device: bool = False, seeds: Optional[List[int]] = None,
                   cfg_split_group=None):
@@ -227,28 +258,8 @@ class Navigator:
         F, H, W = self.num_frames, self.image_height, self.image_width
         sched = EulerSchedule(self.num_inference_steps)
         out = torch.empty((b, F, 3, H, W), dtype=torch.uint8, device=dev)
-        # The reference feeds the observation AS SENT (384x384 / 480x480 from the solvers) to _encode_image, whose antialiased
-        # resize goes straight to 224x224 (pipeline :192-200), and separately resizes the PIL image to (W, H) with LANCZOS in
-        # uint8 for the VAE branch (video_processor.preprocess, DP/image_processor.py:501; pipeline :520).
-        obs = torch.from_numpy(np.ascontiguousarray(images_u8[:, :3])).to(dev)               # uint8 [b, 3, Hin, Win]
-        emb = frontend.encode_image_clip(obs.float() / 255.0, self.image_encoder)             # pil_to_numpy/numpy_to_pt: [0,1]; [b, 1, D]
-        if tuple(obs.shape[-2:]) != (H, W):
-            key = (int(obs.shape[-2]), int(obs.shape[-1]), H, W)
-            if getattr(self, "_obs_resizer_key", None) != key:
-                from .resize import GpuResizer
-                self._obs_resizer, self._obs_resizer_key = GpuResizer(*key, device=dev, requant=False, filt="lanczos"), key
-            obs = self._obs_resizer(obs)
-        pre = (obs.float() / 255.0) * 2.0 - 1.0                                              # video_processor.preprocess: normalize
-        if seeds is not None:
-            # sharded serving: one generator state per branch, so a branch's noise does not depend on which rank rolls it out
-            gens = [torch.Generator(device=dev).manual_seed(int(sd)) for sd in seeds]
-            noise = torch.stack([torch.randn(pre.shape[1:], generator=g, device=dev, dtype=pre.dtype) for g in gens])
-        else:
-            noise = torch.randn(pre.shape, generator=self.generator, device=dev, dtype=pre.dtype)   # pipeline :521-523
-        if self.vae_enc is not None:
-            image_latents = self.vae_enc.encode_mode(pre + self.noise_aug_strength * noise)
-        else:
-            image_latents = frontend.vae_encode_mode(self.vae_encoder_sd, pre + self.noise_aug_strength * noise).to(torch.float16)
+        gens = [torch.Generator(device=dev).manual_seed(int(sd)) for sd in seeds] if seeds is not None else None
+        emb, image_latents = self.encode_observation(images_u8, gens)
         if latents is None and seeds is not None:
             raw = torch.stack([torch.randn((F, 4, H // 8, W // 8), generator=g, device=dev, dtype=torch.float16) for g in gens])
             diag = torch.diagonal(actions, dim1=-2, dim2=-1)
