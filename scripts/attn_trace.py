@@ -19,9 +19,13 @@ buf = (ctypes.c_longlong * (8 * 16))()
 assert lib.wiw_debug_attn_trace(0, buf) == 0
 v = [[buf[i * 16 + k] for k in range(16)] for i in range(8)]
 t0 = min(x for row in v for x in row if x)
-names = ["mma:P0", "mma:iss0", "mma:P1", "mma:iss1", "pri0:S", "pri0:max", "hlp0:go", "pri0:P", "pri1:S", "pri1:max", "hlp1:go", "pri1:P", "hlp0:P", "hlp1:P"]
-print("iter " + " ".join(f"{n:>9s}" for n in names))
+ts = os.environ.get("WIW_ATTN_TS", "3")
+if ts == "2":
+    names = ["mma:P0", "mma:iss0", "mma:P1", "mma:iss1", "pri0:S", "pri0:max", "hlp0:go", "pri0:P", "pri1:S", "pri1:max", "hlp1:go", "pri1:P", "hlp0:P", "hlp1:P"]
+else:   # ts3: two 64-key steps (even | odd) per row; per step: MMA saw P0, issued 0, saw P1, issued 1, primary0 saw S, stored P, primary1 saw S, stored P
+    names = [f"{e}:{n}" for e in ("e", "o") for n in ("mP0", "mI0", "mP1", "mI1", "p0S", "p0P", "p1S", "p1P")]
+print("iter " + " ".join(f"{n:>8s}" for n in names))
 for i, row in enumerate(v):
-    print(f"{i:4d} " + " ".join(f"{(row[k] - t0) if row[k] else -1:9d}" for k in range(14)))
+    print(f"{i:4d} " + " ".join(f"{(row[k] - t0) if row[k] else -1:8d}" for k in range(len(names))))
 per = [(v[i + 1][0] - v[i][0]) for i in range(7)]
-print("cycles per KV tile (mma:P0 to mma:P0):", per)
+print("cycles per 128 keys (slot 0 to slot 0):", per)

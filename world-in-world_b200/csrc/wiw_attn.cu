@@ -996,6 +996,303 @@ attn_spatial_ts2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
     }
 }
 
+
+// =====================================================================================================================
+// TS-mode, two threads per row, 64-key KV steps with DOUBLE-BUFFERED scores.
+//
+// The pipeline timeline of attn_spatial_ts2_kernel (profiles/r02_attn_trace_ts2.txt, cycles per 128-key tile of one Q tile):
+//   S seen -> pass 1 done 743 -> P stored 2001 -> MMA warp sees P 2077 -> PV + next QK issued 2709 (the issuing thread is throttled
+//   to the tensor pipe's execution rate) -> next S seen 3067
+// i.e. softmax (1965) and the MMA phase (1066: PV then the next QK^T, plus two barrier hops) of ONE Q tile are strictly serial, the
+// two Q tiles only fill each other's MMA phase, and MUFU sits at 55 %.  Here the scores of a Q tile live in two 64-column TMEM
+// buffers: while the softmax threads work on S_t(j) in buffer j & 1, QK^T(t, j+1) has already been issued into the other buffer
+// (right behind PV(t, j-1), which vacated it -- in-order tensor pipe), so a finished softmax step finds its next scores ready and
+// both Q tiles keep the exp / issue pipes busy at the same time.
+//   MMA warp, step j, tile t:  wait P_t(j) -> PV(t, j) -> QK^T(t, j+2) into buffer j & 1 -> commit "S index j+2" (real or virtual)
+//   "S index i ready" also means PV(t, i-2) has retired, which is what the lazy O rescale of step i-1 and the epilogue wait for.
+// TMEM columns: S_t buffers at t*128 + {0, 64} (P aliased: primary keys 0..31 -> [0,16), helper keys 32..63 -> [32,48));
+//               O_t at 256 + t*128 (80 columns);  Q_t at 352 + t*128 (32 columns).
+constexpr int kKV3 = 64;
+constexpr int kTileKV3 = kKV3 * kD * 2;                                     // 8 KB K / V tile
+constexpr int kRing3 = 12;
+constexpr int kAttnSmemTS3 = 1024 + 2 * kTileBytes + kRing3 * kTileKV3 + kTileKV3 + 1024 + 512;   // Q0,Q1 | ring | ones | m_ref | barriers
+
+template <int POLY>
+__global__ void __launch_bounds__(kAttnThreads2, 1)
+attn_spatial_ts3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
+                        const __grid_constant__ CUtensorMap tm_out, const __grid_constant__ AttnArgs a, int C) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t sQ = base;                                    // 2 tiles; reused as the O staging tiles of the epilogue
+    const uint32_t sRing = sQ + 2 * kTileBytes;
+    const uint32_t sOnes = sRing + kRing3 * kTileKV3;            // [64][64] fp16 ones: the extra N-atom of the PV B operand
+    const uint32_t sMref = sOnes + kTileKV3;                     // float [2][128]
+    const uint32_t bars = sMref + 1024;
+    const uint32_t bar_q = bars;
+    const uint32_t bar_full = bars + 8;                          // [kRing3]
+    const uint32_t bar_empty = bar_full + 8 * kRing3;            // [kRing3]
+    const uint32_t bar_s_full = bar_empty + 8 * kRing3;          // [tile][buffer]
+    const uint32_t bar_p_full = bar_s_full + 32;                 // [tile][buffer], 256 arrivals
+    const uint32_t bar_q_ready = bar_p_full + 32;                // [2], 256 arrivals
+    const uint32_t tmem_slot = bar_q_ready + 16;
+    uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q0 = blockIdx.x * 2 * kQ, head = blockIdx.y, img = blockIdx.z;
+    const int nkv = a.nkv;                                       // 64-key steps
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tm_q);
+        tma_prefetch_desc(&tm_kv);
+        tma_prefetch_desc(&tm_out);
+        mbar_init(bar_q, 1);
+        for (int i = 0; i < kRing3; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 1); }
+        for (int i = 0; i < 4; ++i) { mbar_init(bar_s_full + 8 * i, 1); mbar_init(bar_p_full + 8 * i, 256); }
+        for (int t = 0; t < 2; ++t) mbar_init(bar_q_ready + 8 * t, 256);
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, kTmemCols);
+        tmem_relinquish();
+    }
+    for (int i = threadIdx.x; i < kTileKV3 / 16; i += kAttnThreads2)
+        *reinterpret_cast<uint4*>(gen + (sOnes - base) + i * 16) = make_uint4(0x3C003C00u, 0x3C003C00u, 0x3C003C00u, 0x3C003C00u);
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gen + (tmem_slot - base));
+
+    if (warp == 0) {
+        // ================================ TMA producer: K_0, K_1, then per step V_j, K_{j+2} ================================
+        if (elect_one()) {
+            mbar_expect_tx(bar_q, 2 * kTileBytes);
+            tma_load_3d(sQ, &tm_q, bar_q, head * kD, q0, img);
+            tma_load_3d(sQ + kTileBytes, &tm_q, bar_q, head * kD, q0 + kQ, img);
+        }
+        __syncwarp();
+        int cnt = 0;
+        auto load = [&](int col, int key0) {
+            const int st = cnt % kRing3;
+            mbar_wait(bar_empty + 8 * st, ((uint32_t)(cnt / kRing3) & 1u) ^ 1u);
+            if (elect_one()) {
+                mbar_expect_tx(bar_full + 8 * st, kTileKV3);
+                tma_load_3d(sRing + st * kTileKV3, &tm_kv, bar_full + 8 * st, col + head * kD, key0, img);
+            }
+            __syncwarp();
+            ++cnt;
+        };
+        load(C, 0);
+        if (nkv > 1) load(C, kKV3);
+        for (int j = 0; j < nkv; ++j) {
+            load(2 * C, j * kKV3);
+            if (j + 2 < nkv) load(C, (j + 2) * kKV3);
+        }
+    } else if (warp == 1) {
+        // ================================ MMA issuer ================================
+        const uint32_t idesc_qk = make_idesc_f16(kKV3, 0, 0);
+        const uint32_t idesc_pv = make_idesc_f16(kOCols, 0, 1);               // B (= [V | ones]) is MN-major, N = 80
+        auto issue_qk = [&](int t, int b, int stage) {                       // S_t[b] = Q_t[tmem] K^T[smem]
+            const uint64_t dk = make_desc_sw128(sRing + stage * kTileKV3);
+            if (elect_one()) {
+#pragma unroll
+                for (int kk = 0; kk < kD / 16; ++kk)
+                    umma_f16_ts(tmem_base + t * 128 + b * 64, tmem_base + kColQ + t * kColStride + 8 * kk, dk + 2 * kk, idesc_qk, kk > 0 ? 1u : 0u);
+            }
+            __syncwarp();
+        };
+        auto issue_pv = [&](int t, int b, int stage, bool first) {           // O_t += P_t[b][tmem] [V | ones][smem]
+            const uint32_t v_addr = sRing + stage * kTileKV3;
+            const uint64_t dv = (uint64_t((v_addr & 0x3FFFF) >> 4)) | (uint64_t((sOnes - v_addr) >> 4) << 16) |
+                                (uint64_t(1024 >> 4) << 32) | (uint64_t(1) << 46) | (uint64_t(2) << 61);
+            if (elect_one()) {
+#pragma unroll
+                for (int kk = 0; kk < kKV3 / 16; ++kk)          // keys 0..31 in P columns [0,16), keys 32..63 in [32,48)
+                    umma_f16_ts(tmem_base + kColO + t * kColStride, tmem_base + t * 128 + b * 64 + (kk >> 1) * 32 + 8 * (kk & 1),
+                                dv + (uint64_t)kk * (2048 >> 4), idesc_pv, (!first || kk > 0) ? 1u : 0u);
+            }
+            __syncwarp();
+        };
+        auto commit = [&](uint32_t bar) {
+            if (elect_one()) umma_commit(bar);
+            __syncwarp();
+        };
+        int cnt = 0;
+        auto next_slot = [&]() {                                             // waits for the next ring item, returns its slot
+            const int st = cnt % kRing3;
+            mbar_wait(bar_full + 8 * st, (uint32_t)(cnt / kRing3) & 1u);
+            ++cnt;
+            return st;
+        };
+        mbar_wait(bar_q_ready + 0, 0);
+        mbar_wait(bar_q_ready + 8, 0);
+        for (int b = 0; b < 2 && b < nkv; ++b) {                             // prologue: S_t(0) -> buffer 0, S_t(1) -> buffer 1
+            const int sk = next_slot();
+            tc_fence_after();
+            for (int t = 0; t < 2; ++t) {
+                issue_qk(t, b, sk);
+                commit(bar_s_full + 8 * (2 * t + b));
+            }
+            commit(bar_empty + 8 * sk);
+        }
+        for (int j = 0; j < nkv; ++j) {
+            const int b = j & 1;
+            const bool more2 = (j + 2 < nkv);
+            const int sv = next_slot();                                      // V_j
+            const int sk = more2 ? next_slot() : 0;                          // K_{j+2}
+            for (int t = 0; t < 2; ++t) {
+                mbar_wait(bar_p_full + 8 * (2 * t + b), (uint32_t)(j >> 1) & 1u);   // P_t(j) in TMEM, every read of S_t(j) done
+                trace_stamp(a, j >> 1, (j & 1) * 8 + 0 + 2 * t);
+                tc_fence_after();
+                issue_pv(t, b, sv, j == 0);
+                if (more2) issue_qk(t, b, sk);                               // behind PV(t, j) in issue order: overwrites S_t[b] | P_t[b]
+                commit(bar_s_full + 8 * (2 * t + b));                        // "S index j+2" (virtual past the end): PV(t, j) retired
+                trace_stamp(a, j >> 1, (j & 1) * 8 + 1 + 2 * t);
+            }
+            commit(bar_empty + 8 * sv);
+            if (more2) commit(bar_empty + 8 * sk);
+        }
+    } else {
+        // ================= softmax: tile t, primary (hf = 0) / helper (hf = 1) thread of one query row =================
+        const int sidx = warp - 2;
+        const int t = sidx >> 3;
+        const int hf = (sidx >> 2) & 1;
+        const int qd = warp & 3;
+        const int row = qd * 32 + lane;
+        const uint32_t lane_sel = (uint32_t)(qd * 32) << 16;
+        const uint32_t tS0 = tmem_base + t * 128 + lane_sel, tO = tmem_base + kColO + t * kColStride + lane_sel;
+        const uint32_t sw = (uint32_t)row & 7u;
+        uint8_t* pQ = gen + (sQ - base) + t * kTileBytes + row * 128;
+        volatile float* mref = reinterpret_cast<volatile float*>(gen + (sMref - base)) + t * 128 + row;
+        // ---- Q row: TMA tile -> registers -> TMEM; each of the two threads copies half of the row
+        mbar_wait(bar_q, 0);
+        {
+            uint32_t r[16];
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch) {
+                const uint4 u = *reinterpret_cast<const uint4*>(pQ + (((uint32_t)(hf * 4 + ch) ^ sw) << 4));
+                r[4 * ch] = u.x; r[4 * ch + 1] = u.y; r[4 * ch + 2] = u.z; r[4 * ch + 3] = u.w;
+            }
+            tmem_st_32x32b_x16(tmem_base + kColQ + t * kColStride + hf * 16 + lane_sel, r);
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(bar_q_ready + 8 * t);
+        }
+        float m_ref = -INFINITY;
+        const float c = a.scale_log2;
+        for (int j = 0; j < nkv; ++j) {
+            const int b = j & 1;
+            const int valid = a.S - j * kKV3;
+            const bool masked = valid < kKV3;
+            const uint32_t tS = tS0 + b * 64;
+            float mc;
+            if (hf == 0) {
+                mbar_wait(bar_s_full + 8 * (2 * t + b), (uint32_t)(j >> 1) & 1u);     // S index j
+                if (qd == 2) trace_stamp(a, j >> 1, (j & 1) * 8 + 4 + 2 * t);
+                tc_fence_after();
+                float mx = -INFINITY;
+                {
+                    uint32_t ra[32], rb[32];
+                    tmem_ld_32x32b_x32(tS, ra);
+                    tmem_ld_32x32b_x32(tS + 32, rb);
+                    tmem_ld_wait();
+                    if (masked) { mask_chunk(ra, 0, valid); mask_chunk(rb, 32, valid); }
+                    mx = row_max_chunk(ra, mx);
+                    mx = row_max_chunk(rb, mx);
+                }
+                const bool grow = (mx - m_ref) * c > kRescaleThreshold;
+                const bool any_grow = __any_sync(0xffffffffu, grow) || (j == 0);
+                float alpha = 1.f;
+                if (any_grow) {
+                    const float m_new = fmaxf(m_ref, mx);
+                    alpha = (m_ref == -INFINITY) ? 0.f : fast_exp2((m_ref - m_new) * c);
+                    m_ref = m_new;
+                }
+                mc = m_ref * c;
+                *mref = mc;                                      // hand-off to the helper thread of this row
+                tc_fence_before();
+                if (t == 0) asm volatile("bar.arrive 1, 256;" ::: "memory");
+                else        asm volatile("bar.arrive 2, 256;" ::: "memory");
+                if (any_grow && j > 0) {
+                    // O_t must be idle: "S index j+1 ready" was committed behind PV(t, j-1)
+                    mbar_wait(bar_s_full + 8 * (2 * t + (b ^ 1)), (uint32_t)((j + 1) >> 1) & 1u);
+                    tc_fence_after();
+#pragma unroll
+                    for (int ch = 0; ch < kOCols / 16; ++ch) {
+                        uint32_t r[16];
+                        tmem_ld_32x32b_x16(tO + ch * 16, r);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) r[e] = __float_as_uint(__uint_as_float(r[e]) * alpha);
+                        tmem_st_32x32b_x16(tO + ch * 16, r);
+                    }
+                }
+            } else {
+                if (t == 0) asm volatile("bar.sync 1, 256;" ::: "memory");
+                else        asm volatile("bar.sync 2, 256;" ::: "memory");
+                tc_fence_after();
+                mc = *mref;
+            }
+            // exponentials of this thread's 32 keys -> 16 packed words at the start of its own 32 score columns
+            {
+                uint32_t r[32], p[16];
+                tmem_ld_32x32b_x32(tS + hf * 32, r);
+                tmem_ld_wait();
+                if (masked) mask_chunk(r, hf * 32, valid);
+                exp_pack<POLY>(r, c, mc, p);
+                tmem_st_32x32b_x16(tS + hf * 32, p);
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(bar_p_full + 8 * (2 * t + b));
+            if (qd == 2 && hf == 0) trace_stamp(a, j >> 1, (j & 1) * 8 + 5 + 2 * t);
+        }
+        // ---- epilogue: "S index nkv+1" == PV(t, nkv-1) retired
+        mbar_wait(bar_s_full + 8 * (2 * t + ((nkv + 1) & 1)), (uint32_t)((nkv + 1) >> 1) & 1u);
+        tc_fence_after();
+        float inv;
+        {
+            uint32_t r[16];
+            tmem_ld_32x32b_x16(tO + 64, r);
+            tmem_ld_wait();
+            inv = 1.f / __uint_as_float(r[0]);
+        }
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch) {
+            uint32_t r[16];
+            tmem_ld_32x32b_x16(tO + (hf * 2 + ch) * 16, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int v8 = 0; v8 < 2; ++v8) {
+                uint4 u;
+                __half2* hh = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    hh[e] = __floats2half2_rn(__uint_as_float(r[v8 * 8 + 2 * e]) * inv, __uint_as_float(r[v8 * 8 + 2 * e + 1]) * inv);
+                const uint32_t chunk16 = (uint32_t)((hf * 2 + ch) * 2 + v8);
+                *reinterpret_cast<uint4*>(pQ + ((chunk16 ^ sw) << 4)) = u;
+            }
+        }
+        fence_proxy_async_smem();
+        if (t == 0) asm volatile("bar.sync 3, 256;" ::: "memory");
+        else        asm volatile("bar.sync 4, 256;" ::: "memory");
+        if (hf == 0 && qd == 2 && lane == 0) {                    // warps 2 and 10
+            asm volatile(
+                "cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
+                ::"l"(reinterpret_cast<uint64_t>(&tm_out)), "r"(sQ + t * kTileBytes), "r"(head * kD), "r"(q0 + t * kQ), "r"(img) : "memory");
+            tma_store_commit();
+            tma_store_wait_all<0>();
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        tc_fence_after();
+        tmem_dealloc(tmem_base, kTmemCols);
+    }
+}
+
 }  // namespace wiw
 
 using namespace wiw;
@@ -1033,6 +1330,13 @@ extern "C" int wiw_attention_spatial(const void* qkv, void* out, int images, int
         uint32_t box[3] = {64, 128, 1};
         if (encode_tmap(&tm_out, out, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return 3;
     }
+    CUtensorMap tm_kv;
+    {
+        uint64_t dims[3] = {(uint64_t)3 * C, (uint64_t)S, (uint64_t)images};
+        uint64_t strides[2] = {(uint64_t)3 * C * 2, (uint64_t)S * 3 * C * 2};
+        uint32_t box[3] = {64, (uint32_t)kKV3, 1};
+        if (encode_tmap(&tm_kv, qkv, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return 3;
+    }
     AttnArgs a;
     a.S = S;
     a.nkv = (S + kKV - 1) / kKV;
@@ -1045,13 +1349,19 @@ extern "C" int wiw_attention_spatial(const void* qkv, void* out, int images, int
         WIW_CHECK_CUDA(cudaFuncSetAttribute(attn_spatial_ts_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemTS));
         WIW_CHECK_CUDA(cudaFuncSetAttribute(attn_spatial_ts2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemTS2));
         WIW_CHECK_CUDA(cudaFuncSetAttribute(attn_spatial_ts2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemTS2));
+        WIW_CHECK_CUDA(cudaFuncSetAttribute(attn_spatial_ts3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemTS3));
+        WIW_CHECK_CUDA(cudaFuncSetAttribute(attn_spatial_ts3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemTS3));
     }
     // development switches for same-box A/B runs: WIW_ATTN_TS=0 -> the shared-memory-operand kernel; WIW_ATTN_POLY = exponential
     // pairs (of every 4) evaluated on the FMA pipe instead of MUFU (see exp2_poly)
-    static const int ts = getenv("WIW_ATTN_TS") ? atoi(getenv("WIW_ATTN_TS")) : 2;        // 0 = SS kernel, 1 = TS 8 softmax warps, 2 = TS 16
+    static const int ts = getenv("WIW_ATTN_TS") ? atoi(getenv("WIW_ATTN_TS")) : 3;        // 0 = SS kernel, 1 = TS 8 softmax warps, 2 = TS 16, 3 = TS 16 + double-buffered 64-key scores
     static const int poly = getenv("WIW_ATTN_POLY") ? atoi(getenv("WIW_ATTN_POLY")) : 1;
     dim3 grid((S + 2 * kQ - 1) / (2 * kQ), C / 64, images);
-    if (!ts) attn_spatial_kernel<1><<<grid, kAttnThreads, kAttnSmem, stream>>>(tm_qkv, tm_out, a, C);
+    if (ts == 3) {
+        a.nkv = (S + kKV3 - 1) / kKV3;
+        if (poly == 2) attn_spatial_ts3_kernel<2><<<grid, kAttnThreads2, kAttnSmemTS3, stream>>>(tm_qkv, tm_kv, tm_out, a, C);
+        else attn_spatial_ts3_kernel<1><<<grid, kAttnThreads2, kAttnSmemTS3, stream>>>(tm_qkv, tm_kv, tm_out, a, C);
+    } else if (!ts) attn_spatial_kernel<1><<<grid, kAttnThreads, kAttnSmem, stream>>>(tm_qkv, tm_out, a, C);
     else if (ts == 2 && poly == 2) attn_spatial_ts2_kernel<2><<<grid, kAttnThreads2, kAttnSmemTS2, stream>>>(tm_qkv, tm_out, a, C);
     else if (ts == 2) attn_spatial_ts2_kernel<1><<<grid, kAttnThreads2, kAttnSmemTS2, stream>>>(tm_qkv, tm_out, a, C);
     else if (poly == 2) attn_spatial_ts_kernel<2><<<grid, kAttnThreads, kAttnSmemTS, stream>>>(tm_qkv, tm_out, a, C);
