@@ -19,9 +19,11 @@ buf = (ctypes.c_longlong * (8 * 16))()
 assert lib.wiw_debug_attn_trace(0, buf) == 0
 v = [[buf[i * 16 + k] for k in range(16)] for i in range(8)]
 t0 = min(x for row in v for x in row if x)
-ts = os.environ.get("WIW_ATTN_TS", "3")
+ts = os.environ.get("WIW_ATTN_TS", "4")
 if ts == "2":
     names = ["mma:P0", "mma:iss0", "mma:P1", "mma:iss1", "pri0:S", "pri0:max", "hlp0:go", "pri0:P", "pri1:S", "pri1:max", "hlp1:go", "pri1:P", "hlp0:P", "hlp1:P"]
+elif ts == "4":   # one Q tile, 128-key steps: MMA warp saw P(j) | issued PV(j) + QK(j+2) + commit | softmax saw S(j) | row max known | P(j) stored
+    names = ["mma:P", "mma:iss", "smx:S", "smx:max", "smx:P"]
 else:   # ts3: two 64-key steps (even | odd) per row; per step: MMA saw P0, issued 0, saw P1, issued 1, primary0 saw S, stored P, primary1 saw S, stored P
     names = [f"{e}:{n}" for e in ("e", "o") for n in ("mP0", "mI0", "mP1", "mI1", "p0S", "p0P", "p1S", "p1P")]
 print("iter " + " ".join(f"{n:>8s}" for n in names))

@@ -61,6 +61,8 @@ struct AttnArgs {
     int S, nkv;
     float scale_log2;                            // (1/sqrt(d)) * log2(e)
     long long* trace;                            // development aid (wiw_debug_attn_trace): clock64 stamps of CTA 0, else null
+    int dbg;                                     // development aid (WIW_ATTN_DBG, ts3 only; results are garbage): bit 0 = softmax threads skip
+                                                 // their TMEM loads / exponentials / stores, bit 1 = the MMA warp skips the MMAs (commits only)
 };
 constexpr int kTraceIters = 8, kTraceFirst = 16, kTraceSlots = 16;      // stamps of KV tiles [16, 24): [iter][slot]
 __device__ __forceinline__ void trace_stamp(const AttnArgs& a, int j, int slot) {
@@ -1094,7 +1096,7 @@ attn_spatial_ts3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
         const uint32_t idesc_pv = make_idesc_f16(kOCols, 0, 1);               // B (= [V | ones]) is MN-major, N = 80
         auto issue_qk = [&](int t, int b, int stage) {                       // S_t[b] = Q_t[tmem] K^T[smem]
             const uint64_t dk = make_desc_sw128(sRing + stage * kTileKV3);
-            if (elect_one()) {
+            if (!(a.dbg & 2) && elect_one()) {
 #pragma unroll
                 for (int kk = 0; kk < kD / 16; ++kk)
                     umma_f16_ts(tmem_base + t * 128 + b * 64, tmem_base + kColQ + t * kColStride + 8 * kk, dk + 2 * kk, idesc_qk, kk > 0 ? 1u : 0u);
@@ -1105,7 +1107,7 @@ attn_spatial_ts3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
             const uint32_t v_addr = sRing + stage * kTileKV3;
             const uint64_t dv = (uint64_t((v_addr & 0x3FFFF) >> 4)) | (uint64_t((sOnes - v_addr) >> 4) << 16) |
                                 (uint64_t(1024 >> 4) << 32) | (uint64_t(1) << 46) | (uint64_t(2) << 61);
-            if (elect_one()) {
+            if (!(a.dbg & 2) && elect_one()) {
 #pragma unroll
                 for (int kk = 0; kk < kKV3 / 16; ++kk)          // keys 0..31 in P columns [0,16), keys 32..63 in [32,48)
                     umma_f16_ts(tmem_base + kColO + t * kColStride, tmem_base + t * 128 + b * 64 + (kk >> 1) * 32 + 8 * (kk & 1),
@@ -1191,7 +1193,8 @@ attn_spatial_ts3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
                 if (qd == 2) trace_stamp(a, j >> 1, (j & 1) * 8 + 4 + 2 * t);
                 tc_fence_after();
                 float mx = -INFINITY;
-                {
+                if (a.dbg & 1) mx = 1.f;
+                else {
                     uint32_t ra[32], rb[32];
                     tmem_ld_32x32b_x32(tS, ra);
                     tmem_ld_32x32b_x32(tS + 32, rb);
@@ -1234,7 +1237,7 @@ attn_spatial_ts3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
                 mc = *mref;
             }
             // exponentials of this thread's 32 keys -> 16 packed words at the start of its own 32 score columns
-            {
+            if (!(a.dbg & 1)) {
                 uint32_t r[32], p[16];
                 tmem_ld_32x32b_x32(tS + hf * 32, r);
                 tmem_ld_wait();
@@ -1280,6 +1283,293 @@ attn_spatial_ts3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
             asm volatile(
                 "cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
                 ::"l"(reinterpret_cast<uint64_t>(&tm_out)), "r"(sQ + t * kTileBytes), "r"(head * kD), "r"(q0 + t * kQ), "r"(img) : "memory");
+            tma_store_commit();
+            tma_store_wait_all<0>();
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        tc_fence_after();
+        tmem_dealloc(tmem_base, kTmemCols);
+    }
+}
+
+
+// =====================================================================================================================
+// ts4: ONE 128-row Q tile per CTA, FOUR threads per query row, 128-key steps with double-buffered scores, single-pass softmax.
+//
+// What the timing switches of ts3 showed (profiles/r02_attn_ts3_bounds.txt, cycles per 128 keys of two Q tiles): full kernel 3 900,
+// MMAs only 2 990, softmax only 3 090, NEITHER (barriers, commits and TMA only) 2 170 -- the synchronisation skeleton itself is the
+// bound: every tcgen05.commit costs the issuing warp ~200 cycles and every (already complete) mbarrier try_wait ~90, and the one MMA
+// warp served two Q tiles x two 64-key steps with 8 commits + 8 waits per 128 keys.  This variant keeps the ideas that are sound
+// (A operands in TMEM, P aliased on S, next QK^T issued behind the current PV into the other score buffer) and minimises the
+// hand-offs:
+//   * one Q tile, so the MMA warp does ONE commit and three waits per 128-key step: wait V_j -> wait P(j) -> PV(j) -> wait K_{j+2}
+//     -> QK^T(j+2) -> commit "S index j+2".  K/V ring slots are released by a softmax thread when it observes "S index j+2"
+//     (that commit sits behind PV(j) and QK^T(j+2) in issue order), not by extra commits;
+//   * sixteen softmax warps on the same 128 rows: thread (role q, row r) owns keys 32q..32q+31 of row r.  It loads its 32 scores ONCE,
+//     publishes its partial row max through shared memory, one 512-thread named barrier, reads the four partials -> the row max
+//     and (identically in all four threads of the row) the reference-max / lazy-rescale decision, exponentiates its 32 scores from
+//     registers and stores 16 packed words over the start of its own score columns.  No second TMEM sweep, no primary / helper
+//     asymmetry, 4 warps per SM sub-partition.
+// TMEM columns: S buffers [0,128) and [128,256) (P of role q at buffer + 32q .. +16), O [256,336), Q [352,384).
+constexpr int kRing4 = 8;
+constexpr int kAttnThreads4 = 18 * 32;
+constexpr int kAttnSmemTS4 = 1024 + kTileBytes * (1 + kRing4 + 1) + 4096 + 512;      // Q | K/V ring | ones | partial maxima [2][4][128] | barriers
+
+__device__ __forceinline__ int ring_pos_v(int j, int nkv) { return min(nkv, 2) + j + min(j, max(nkv - 2, 0)); }
+__device__ __forceinline__ int ring_pos_k(int i, int nkv) { return i < 2 ? i : ring_pos_v(i - 2, nkv) + 1; }
+
+template <int POLY>
+__global__ void __launch_bounds__(kAttnThreads4, 1)
+attn_spatial_ts4_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_out,
+                        const __grid_constant__ AttnArgs a, int C) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t sQ = base;                                    // Q tile; reused as the O staging tile of the epilogue
+    const uint32_t sRing = sQ + kTileBytes;
+    const uint32_t sOnes = sRing + kRing4 * kTileBytes;
+    const uint32_t sMax = sOnes + kTileBytes;                    // float [2 (step parity)][4 roles][128 rows]
+    const uint32_t bars = sMax + 4096;
+    const uint32_t bar_q = bars;
+    const uint32_t bar_full = bars + 8;                          // [kRing4]
+    const uint32_t bar_empty = bar_full + 8 * kRing4;            // [kRing4]  one arrival (a softmax thread)
+    const uint32_t bar_s_full = bar_empty + 8 * kRing4;          // [2 buffers]
+    const uint32_t bar_p_full = bar_s_full + 16;                 // [2 buffers], 512 arrivals
+    const uint32_t bar_q_ready = bar_p_full + 16;                // 256 arrivals (roles 0 and 1 copy Q)
+    const uint32_t tmem_slot = bar_q_ready + 8;
+    uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q0 = blockIdx.x * kQ, head = blockIdx.y, img = blockIdx.z;
+    const int nkv = a.nkv;
+    constexpr uint32_t kColO4 = 256, kColQ4 = 352;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tm_qkv);
+        tma_prefetch_desc(&tm_out);
+        mbar_init(bar_q, 1);
+        for (int i = 0; i < kRing4; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(bar_s_full + 8 * b, 1); mbar_init(bar_p_full + 8 * b, 512); }
+        mbar_init(bar_q_ready, 256);
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, kTmemCols);
+        tmem_relinquish();
+    }
+    for (int i = threadIdx.x; i < kTileBytes / 16; i += kAttnThreads4)
+        *reinterpret_cast<uint4*>(gen + (sOnes - base) + i * 16) = make_uint4(0x3C003C00u, 0x3C003C00u, 0x3C003C00u, 0x3C003C00u);
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gen + (tmem_slot - base));
+
+    if (warp == 0) {
+        // ================================ TMA producer: Q, K_0, K_1, then per step V_j, K_{j+2} ================================
+        if (elect_one()) {
+            mbar_expect_tx(bar_q, kTileBytes);
+            tma_load_3d(sQ, &tm_qkv, bar_q, head * kD, q0, img);
+        }
+        __syncwarp();
+        int cnt = 0;
+        auto load = [&](int col, int key0) {
+            const int st = cnt % kRing4;
+            mbar_wait(bar_empty + 8 * st, ((uint32_t)(cnt / kRing4) & 1u) ^ 1u);
+            if (elect_one()) {
+                mbar_expect_tx(bar_full + 8 * st, kTileBytes);
+                tma_load_3d(sRing + st * kTileBytes, &tm_qkv, bar_full + 8 * st, col + head * kD, key0, img);
+            }
+            __syncwarp();
+            ++cnt;
+        };
+        load(C, 0);
+        if (nkv > 1) load(C, kKV);
+        for (int j = 0; j < nkv; ++j) {
+            load(2 * C, j * kKV);
+            if (j + 2 < nkv) load(C, (j + 2) * kKV);
+        }
+    } else if (warp == 1) {
+        // ================================ MMA issuer ================================
+        const uint32_t idesc_qk = make_idesc_f16(kKV, 0, 0);
+        const uint32_t idesc_pv = make_idesc_f16(kOCols, 0, 1);               // B (= [V | ones]) is MN-major, N = 80
+        auto issue_qk = [&](int b, int stage) {                              // S[b] = Q[tmem] K^T[smem]
+            const uint64_t dk = make_desc_sw128(sRing + stage * kTileBytes);
+            if (!(a.dbg & 2) && elect_one()) {
+#pragma unroll
+                for (int kk = 0; kk < kD / 16; ++kk)
+                    umma_f16_ts(tmem_base + b * 128, tmem_base + kColQ4 + 8 * kk, dk + 2 * kk, idesc_qk, kk > 0 ? 1u : 0u);
+            }
+            __syncwarp();
+        };
+        auto issue_pv = [&](int b, int stage, bool first) {                  // O += P[b][tmem] [V | ones][smem]
+            const uint32_t v_addr = sRing + stage * kTileBytes;
+            const uint64_t dv = (uint64_t((v_addr & 0x3FFFF) >> 4)) | (uint64_t((sOnes - v_addr) >> 4) << 16) |
+                                (uint64_t(1024 >> 4) << 32) | (uint64_t(1) << 46) | (uint64_t(2) << 61);
+            if (!(a.dbg & 2) && elect_one()) {
+#pragma unroll
+                for (int kk = 0; kk < kKV / 16; ++kk)           // keys 32q..32q+31 (role q) in P columns [32q, 32q+16)
+                    umma_f16_ts(tmem_base + kColO4, tmem_base + b * 128 + (kk >> 1) * 32 + 8 * (kk & 1),
+                                dv + (uint64_t)kk * (2048 >> 4), idesc_pv, (!first || kk > 0) ? 1u : 0u);
+            }
+            __syncwarp();
+        };
+        auto commit = [&](uint32_t bar) {
+            if (elect_one()) umma_commit(bar);
+            __syncwarp();
+        };
+        int cnt = 0;
+        auto next_slot = [&]() {
+            const int st = cnt % kRing4;
+            mbar_wait(bar_full + 8 * st, (uint32_t)(cnt / kRing4) & 1u);
+            ++cnt;
+            return st;
+        };
+        mbar_wait(bar_q_ready, 0);
+        for (int b = 0; b < 2 && b < nkv; ++b) {                             // prologue: S(0) -> buffer 0, S(1) -> buffer 1
+            const int sk = next_slot();
+            tc_fence_after();
+            issue_qk(b, sk);
+            commit(bar_s_full + 8 * b);
+        }
+        for (int j = 0; j < nkv; ++j) {
+            const int b = j & 1;
+            const bool more2 = (j + 2 < nkv);
+            const int sv = next_slot();                                      // V_j
+            mbar_wait(bar_p_full + 8 * b, (uint32_t)(j >> 1) & 1u);          // P(j) in TMEM, every read of S(j) done
+            trace_stamp(a, j, 0);
+            tc_fence_after();
+            issue_pv(b, sv, j == 0);
+            if (more2) {
+                const int sk = next_slot();                                  // K_{j+2}
+                tc_fence_after();
+                issue_qk(b, sk);                                             // behind PV(j) in issue order: overwrites S[b] | P[b]
+            }
+            commit(bar_s_full + 8 * b);                                      // "S index j+2" (virtual past the end): PV(j) retired
+            trace_stamp(a, j, 1);
+        }
+    } else {
+        // ================= softmax: thread (role q, row) owns keys 32q..32q+31 of its row in every step =================
+        const int role = (warp - 2) >> 2;
+        const int qd = warp & 3;
+        const int row = qd * 32 + lane;
+        const uint32_t lane_sel = (uint32_t)(qd * 32) << 16;
+        const uint32_t tS0 = tmem_base + lane_sel + role * 32, tO = tmem_base + kColO4 + lane_sel;
+        const uint32_t sw = (uint32_t)row & 7u;
+        uint8_t* pQ = gen + (sQ - base) + row * 128;
+        float* smax = reinterpret_cast<float*>(gen + (sMax - base));
+        const bool releaser = (warp == 2);                       // its elected lane hands ring slots back to the TMA producer
+        // ---- Q row: TMA tile -> registers -> TMEM (roles 0 and 1 copy half a row each)
+        if (role < 2) {
+            mbar_wait(bar_q, 0);
+            uint32_t r[16];
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch) {
+                const uint4 u = *reinterpret_cast<const uint4*>(pQ + (((uint32_t)(role * 4 + ch) ^ sw) << 4));
+                r[4 * ch] = u.x; r[4 * ch + 1] = u.y; r[4 * ch + 2] = u.z; r[4 * ch + 3] = u.w;
+            }
+            tmem_st_32x32b_x16(tmem_base + kColQ4 + role * 16 + lane_sel, r);
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(bar_q_ready);
+        }
+        float m_ref = -INFINITY;
+        const float c = a.scale_log2;
+        for (int j = 0; j < nkv; ++j) {
+            const int b = j & 1;
+            const int valid = a.S - j * kKV;
+            const uint32_t tS = tS0 + b * 128;
+            mbar_wait(bar_s_full + 8 * b, (uint32_t)(j >> 1) & 1u);          // S index j: also PV(j-2) and QK^T(j) have retired
+            if (releaser) {
+                if (elect_one()) {
+                    mbar_arrive(bar_empty + 8 * (ring_pos_k(j, nkv) % kRing4));                      // K_j
+                    if (j >= 2) mbar_arrive(bar_empty + 8 * (ring_pos_v(j - 2, nkv) % kRing4));      // V_{j-2}
+                }
+                __syncwarp();
+                trace_stamp(a, j, 2);
+            }
+            tc_fence_after();
+            uint32_t r[32];
+            float mx;
+            if (a.dbg & 1) {
+                mx = 1.f;
+            } else {
+                tmem_ld_32x32b_x32(tS, r);
+                tmem_ld_wait();
+                if (valid < kKV) mask_chunk(r, role * 32, valid);
+                mx = row_max_chunk(r, -INFINITY);
+            }
+            // partial row maxima through shared memory (double-buffered by step parity), one barrier for the 16 softmax warps
+            float* sm = smax + b * 512;
+            sm[role * 128 + row] = mx;
+            asm volatile("bar.sync 1, 512;" ::: "memory");
+            mx = fmaxf(fmaxf(sm[row], sm[128 + row]), fmaxf(sm[256 + row], sm[384 + row]));
+            if (releaser) trace_stamp(a, j, 3);
+            const bool grow = (mx - m_ref) * c > kRescaleThreshold;
+            const bool any_grow = __any_sync(0xffffffffu, grow) || (j == 0);       // same rows, same maxima: identical in all 4 roles
+            if (any_grow) {
+                const float m_new = fmaxf(m_ref, mx);
+                const float alpha = (m_ref == -INFINITY) ? 0.f : fast_exp2((m_ref - m_new) * c);
+                m_ref = m_new;
+                if (j > 0) {
+                    // O must be idle: "S index j+1" was committed behind PV(j-1).  Role q rescales output columns [16q, 16q+16),
+                    // role 0 also the row-sum columns.
+                    mbar_wait(bar_s_full + 8 * (b ^ 1), (uint32_t)((j + 1) >> 1) & 1u);
+                    tc_fence_after();
+                    uint32_t o[16];
+                    tmem_ld_32x32b_x16(tO + role * 16, o);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
+                    tmem_st_32x32b_x16(tO + role * 16, o);
+                    if (role == 0) {
+                        tmem_ld_32x32b_x16(tO + 64, o);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
+                        tmem_st_32x32b_x16(tO + 64, o);
+                    }
+                }
+            }
+            if (!(a.dbg & 1)) {
+                uint32_t p[16];
+                exp_pack<POLY>(r, c, m_ref * c, p);
+                tmem_st_32x32b_x16(tS, p);                       // over the first 16 of this thread's own 32 score columns
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(bar_p_full + 8 * b);
+            if (releaser) trace_stamp(a, j, 4);
+        }
+        // ---- epilogue: "S index nkv+1" == PV(nkv-1) retired; role q converts output columns [16q, 16q+16)
+        mbar_wait(bar_s_full + 8 * ((nkv + 1) & 1), (uint32_t)((nkv + 1) >> 1) & 1u);
+        tc_fence_after();
+        {
+            uint32_t l[16], o[16];
+            tmem_ld_32x32b_x16(tO + 64, l);                      // row sum l = (P @ ones), fp32 from the tensor core
+            tmem_ld_32x32b_x16(tO + role * 16, o);
+            tmem_ld_wait();
+            const float inv = 1.f / __uint_as_float(l[0]);
+#pragma unroll
+            for (int v8 = 0; v8 < 2; ++v8) {
+                uint4 u;
+                __half2* hh = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    hh[e] = __floats2half2_rn(__uint_as_float(o[v8 * 8 + 2 * e]) * inv, __uint_as_float(o[v8 * 8 + 2 * e + 1]) * inv);
+                const uint32_t chunk16 = (uint32_t)(role * 2 + v8);
+                *reinterpret_cast<uint4*>(pQ + ((chunk16 ^ sw) << 4)) = u;
+            }
+        }
+        fence_proxy_async_smem();
+        asm volatile("bar.sync 2, 512;" ::: "memory");
+        if (warp == 2 && lane == 0) {
+            asm volatile(
+                "cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
+                ::"l"(reinterpret_cast<uint64_t>(&tm_out)), "r"(sQ), "r"(head * kD), "r"(q0), "r"(img) : "memory");
             tma_store_commit();
             tma_store_wait_all<0>();
         }
@@ -1342,6 +1632,8 @@ extern "C" int wiw_attention_spatial(const void* qkv, void* out, int images, int
     a.nkv = (S + kKV - 1) / kKV;
     a.scale_log2 = 0.125f * 1.4426950408889634f;
     a.trace = g_attn_trace;
+    static const int attn_dbg = getenv("WIW_ATTN_DBG") ? atoi(getenv("WIW_ATTN_DBG")) : 0;
+    a.dbg = attn_dbg;
     static unsigned long long attr_set = 0;
     if (first_call_on_device(&attr_set)) {
         WIW_CHECK_CUDA(cudaFuncSetAttribute(attn_spatial_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
@@ -1351,13 +1643,19 @@ extern "C" int wiw_attention_spatial(const void* qkv, void* out, int images, int
         WIW_CHECK_CUDA(cudaFuncSetAttribute(attn_spatial_ts2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemTS2));
         WIW_CHECK_CUDA(cudaFuncSetAttribute(attn_spatial_ts3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemTS3));
         WIW_CHECK_CUDA(cudaFuncSetAttribute(attn_spatial_ts3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemTS3));
+        WIW_CHECK_CUDA(cudaFuncSetAttribute(attn_spatial_ts4_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemTS4));
+        WIW_CHECK_CUDA(cudaFuncSetAttribute(attn_spatial_ts4_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemTS4));
     }
     // development switches for same-box A/B runs: WIW_ATTN_TS=0 -> the shared-memory-operand kernel; WIW_ATTN_POLY = exponential
     // pairs (of every 4) evaluated on the FMA pipe instead of MUFU (see exp2_poly)
-    static const int ts = getenv("WIW_ATTN_TS") ? atoi(getenv("WIW_ATTN_TS")) : 3;        // 0 = SS kernel, 1 = TS 8 softmax warps, 2 = TS 16, 3 = TS 16 + double-buffered 64-key scores
+    static const int ts = getenv("WIW_ATTN_TS") ? atoi(getenv("WIW_ATTN_TS")) : 4;        // 0 = SS kernel, 1 = TS 8 softmax warps, 2 = TS 16, 3 = TS 16 + double-buffered 64-key scores
     static const int poly = getenv("WIW_ATTN_POLY") ? atoi(getenv("WIW_ATTN_POLY")) : 1;
     dim3 grid((S + 2 * kQ - 1) / (2 * kQ), C / 64, images);
-    if (ts == 3) {
+    if (ts == 4) {
+        dim3 grid4((S + kQ - 1) / kQ, C / 64, images);
+        if (poly == 2) attn_spatial_ts4_kernel<2><<<grid4, kAttnThreads4, kAttnSmemTS4, stream>>>(tm_qkv, tm_out, a, C);
+        else attn_spatial_ts4_kernel<1><<<grid4, kAttnThreads4, kAttnSmemTS4, stream>>>(tm_qkv, tm_out, a, C);
+    } else if (ts == 3) {
         a.nkv = (S + kKV3 - 1) / kKV3;
         if (poly == 2) attn_spatial_ts3_kernel<2><<<grid, kAttnThreads2, kAttnSmemTS3, stream>>>(tm_qkv, tm_kv, tm_out, a, C);
         else attn_spatial_ts3_kernel<1><<<grid, kAttnThreads2, kAttnSmemTS3, stream>>>(tm_qkv, tm_kv, tm_out, a, C);
