@@ -1868,6 +1868,296 @@ attn_spatial_ss2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
     }
 }
 
+// =====================================================================================================================
+// ss3 = ss2 + ONE MMA WARP PER Q TILE + ring slots released by the softmax threads.
+// The MMA warp of the kernels above serves both tiles in a fixed order and pays, per KV tile, 6 tcgen05.commit (~200 cycles of
+// issue time each, measured on the barrier-only skeletons: profiles/r02_attn_ts3_bounds.txt) and 6 mbarrier waits (~90 each when
+// already complete) on top of the throttled issue of 24 MMAs: ~2 900 cycles, the iteration time of EVERY variant.  Here each tile's
+// QK^T / PV chain has its own issuing warp (2 commits + 4 waits per KV tile) and the K/V ring is handed back by a softmax thread of
+// each tile once it has observed the commit that covers the slot's last reader.
+// ss2: the shared-memory-operand kernel (attn_spatial_kernel: Q, P in smem, QK^T of the next KV tile issued as soon as the scores
+// are read) with TWO threads per query row: the primary thread (warps 2-5 / 10-13) runs pass 1 over all 128 scores, decides the
+// reference max / lazy rescale and exponentiates keys 0..63; the helper thread (warps 6-9 / 14-17) is released through a named
+// barrier and exponentiates keys 64..127 into the second half of the P tile.  Timeline of the TS variants
+// (profiles/r02_attn_trace_ts2.txt): the exponential phase of a tile shrinks from ~1 800 to ~1 220 cycles with the split, but
+// aliasing P on S delays the next QK^T behind PV (+600 cycles); here P stays in shared memory so both gains combine.
+constexpr int kAttnThreads3 = 19 * 32;
+
+template <int POLY>
+__global__ void __launch_bounds__(kAttnThreads3, 1)
+attn_spatial_ss3_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_out,
+                        const __grid_constant__ AttnArgs a, int C) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t sQ = base;                                    // 2 tiles
+    const uint32_t sRing = sQ + 2 * kTileBytes;
+    const uint32_t sOnes = sRing + kRing * kTileBytes;
+    const uint32_t sP = sOnes + kTileBytes;                      // tile t: 2 x 16 KB at sP + t*32 KB; reused for O staging
+    const uint32_t sMref = sP + 4 * kTileBytes;                  // float [2][128]
+    const uint32_t bars = sMref + 1024;
+    const uint32_t bar_q = bars;
+    const uint32_t bar_full = bars + 8;                          // [kRing]
+    const uint32_t bar_empty = bar_full + 8 * kRing;             // [kRing]
+    const uint32_t bar_s_full = bar_empty + 8 * kRing;           // [2]
+    const uint32_t bar_s_free = bar_s_full + 16;                 // [2]  256 arrivals
+    const uint32_t bar_p_full = bar_s_free + 16;                 // [2]  256 arrivals
+    const uint32_t bar_pv_done = bar_p_full + 16;                // [2]
+    const uint32_t tmem_slot = bar_pv_done + 16;
+    uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q0 = blockIdx.x * 2 * kQ, head = blockIdx.y, img = blockIdx.z;
+    const int nkv = a.nkv;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tm_qkv);
+        tma_prefetch_desc(&tm_out);
+        mbar_init(bar_q, 1);
+        for (int i = 0; i < kRing; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 2); }   // one release per tile
+        for (int t = 0; t < 2; ++t) {
+            mbar_init(bar_s_full + 8 * t, 1);
+            mbar_init(bar_s_free + 8 * t, 256);
+            mbar_init(bar_p_full + 8 * t, 256);
+            mbar_init(bar_pv_done + 8 * t, 1);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, kTmemCols);
+        tmem_relinquish();
+    }
+    for (int i = threadIdx.x; i < kTileBytes / 16; i += kAttnThreads3)
+        *reinterpret_cast<uint4*>(gen + (sOnes - base) + i * 16) = make_uint4(0x3C003C00u, 0x3C003C00u, 0x3C003C00u, 0x3C003C00u);
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gen + (tmem_slot - base));
+
+    if (warp == 0) {
+        // ================================ TMA producer ================================
+        if (elect_one()) {
+            mbar_expect_tx(bar_q, 2 * kTileBytes);
+            tma_load_3d(sQ, &tm_qkv, bar_q, head * kD, q0, img);
+            tma_load_3d(sQ + kTileBytes, &tm_qkv, bar_q, head * kD, q0 + kQ, img);
+        }
+        __syncwarp();
+        for (int i = 0; i < 2 * nkv; ++i) {                     // item 2j = K_j, 2j+1 = V_j
+            const int st = i % kRing;
+            mbar_wait(bar_empty + 8 * st, ((uint32_t)(i / kRing) & 1u) ^ 1u);
+            if (elect_one()) {
+                mbar_expect_tx(bar_full + 8 * st, kTileBytes);
+                const int col = ((i & 1) ? 2 * C : C) + head * kD;
+                tma_load_3d(sRing + st * kTileBytes, &tm_qkv, bar_full + 8 * st, col, (i >> 1) * kKV, img);
+            }
+            __syncwarp();
+        }
+    } else if (warp <= 2) {
+        // ================================ MMA issuer of tile t = warp - 1 ================================
+        const int t = warp - 1;
+        const uint32_t idesc_qk = make_idesc_f16(kKV, 0, 0);
+        const uint32_t idesc_pv = make_idesc_f16(kOCols, 0, 1);
+        auto issue_qk = [&](int stage) {
+            const uint64_t dq = make_desc_sw128(sQ + t * kTileBytes), dk = make_desc_sw128(sRing + stage * kTileBytes);
+            if (elect_one()) {
+#pragma unroll
+                for (int kk = 0; kk < kD / 16; ++kk)
+                    umma_f16_ss(tmem_base + t * 128, dq + 2 * kk, dk + 2 * kk, idesc_qk, kk > 0 ? 1u : 0u);
+                umma_commit(bar_s_full + 8 * t);
+            }
+            __syncwarp();
+        };
+        auto issue_pv = [&](int stage, bool first) {
+            const uint32_t v_addr = sRing + stage * kTileBytes;
+            const uint64_t dv = (uint64_t((v_addr & 0x3FFFF) >> 4)) | (uint64_t((sOnes - v_addr) >> 4) << 16) |
+                                (uint64_t(1024 >> 4) << 32) | (uint64_t(1) << 46) | (uint64_t(2) << 61);
+            const uint64_t dp0 = make_desc_sw128(sP + t * 2 * kTileBytes);
+            if (elect_one()) {
+#pragma unroll
+                for (int kk = 0; kk < kKV / 16; ++kk) {
+                    const uint64_t dp = dp0 + (uint64_t)((kk >> 2) * (kTileBytes >> 4) + 2 * (kk & 3));
+                    umma_f16_ss(tmem_base + 256 + t * 128, dp, dv + (uint64_t)kk * (2048 >> 4), idesc_pv, (!first || kk > 0) ? 1u : 0u);
+                }
+                umma_commit(bar_pv_done + 8 * t);
+            }
+            __syncwarp();
+        };
+        mbar_wait(bar_q, 0);
+        mbar_wait(bar_full + 0, 0);                                           // K_0 in ring slot 0
+        tc_fence_after();
+        issue_qk(0);
+        for (int j = 0; j < nkv; ++j) {
+            const bool more = (j + 1 < nkv);
+            const int ik = 2 * j + 2, iv = 2 * j + 1;
+            const int sk = ik % kRing, sv = iv % kRing;
+            if (more) {
+                mbar_wait(bar_full + 8 * sk, (uint32_t)(ik / kRing) & 1u);    // K_{j+1}
+                mbar_wait(bar_s_free + 8 * t, (uint32_t)j & 1u);              // both threads of every row have read S_t(j)
+                tc_fence_after();
+                issue_qk(sk);
+            }
+            mbar_wait(bar_full + 8 * sv, (uint32_t)(iv / kRing) & 1u);        // V_j
+            mbar_wait(bar_p_full + 8 * t, (uint32_t)j & 1u);                  // P_t(j) is in smem
+            tc_fence_after();
+            issue_pv(sv, j == 0);
+        }
+    } else {
+        // ================= softmax: tile t, primary (hf = 0) / helper (hf = 1) thread of one query row =================
+        const int sidx = warp - 3;
+        const int t = sidx >> 3;
+        const int hf = (sidx >> 2) & 1;
+        const int qd = warp & 3;
+        const int row = qd * 32 + lane;
+        const uint32_t lane_sel = (uint32_t)(qd * 32) << 16;
+        const uint32_t tS = tmem_base + t * 128 + lane_sel, tO = tmem_base + 256 + t * 128 + lane_sel;
+        const uint32_t sw = (uint32_t)row & 7u;
+        uint8_t* pP = gen + (sP - base) + t * 2 * kTileBytes + row * 128;
+        volatile float* mref = reinterpret_cast<volatile float*>(gen + (sMref - base)) + t * 128 + row;
+        float m_ref = -INFINITY;
+        const float c = a.scale_log2;
+        const bool releaser = (sidx & 7) == 0;                   // first primary warp of the tile: hands ring slots back to the TMA producer
+        for (int j = 0; j < nkv; ++j) {
+            const int valid = a.S - j * kKV;
+            const bool masked = valid < kKV;
+            float mc, alpha = 1.f;
+            bool rescale = false;
+            if (hf == 0) {
+                mbar_wait(bar_s_full + 8 * t, (uint32_t)j & 1u);
+                if (releaser) {                                  // QK^T(t, j) has retired: this tile is done with K_j
+                    if (elect_one()) mbar_arrive(bar_empty + 8 * ((2 * j) % kRing));
+                    __syncwarp();
+                }
+                tc_fence_after();
+                float mx = -INFINITY;
+                if (!masked) {
+                    uint32_t ra[32], rb[32];
+                    tmem_ld_32x32b_x32(tS, ra);
+                    tmem_ld_wait();
+                    tmem_ld_32x32b_x32(tS + 32, rb);
+                    mx = row_max_chunk(ra, mx);
+                    tmem_ld_wait();
+                    tmem_ld_32x32b_x32(tS + 64, ra);
+                    mx = row_max_chunk(rb, mx);
+                    tmem_ld_wait();
+                    tmem_ld_32x32b_x32(tS + 96, rb);
+                    mx = row_max_chunk(ra, mx);
+                    tmem_ld_wait();
+                    mx = row_max_chunk(rb, mx);
+                } else {
+#pragma unroll 1
+                    for (int ch = 0; ch < 4; ++ch) {
+                        uint32_t r[32];
+                        tmem_ld_32x32b_x32(tS + ch * 32, r);
+                        tmem_ld_wait();
+                        mask_chunk(r, ch * 32, valid);
+                        mx = row_max_chunk(r, mx);
+                    }
+                }
+                const bool grow = (mx - m_ref) * c > kRescaleThreshold;
+                const bool any_grow = __any_sync(0xffffffffu, grow) || (j == 0);
+                if (any_grow) {
+                    const float m_new = fmaxf(m_ref, mx);
+                    alpha = (m_ref == -INFINITY) ? 0.f : fast_exp2((m_ref - m_new) * c);
+                    m_ref = m_new;
+                    rescale = (j > 0);
+                }
+                mc = m_ref * c;
+                *mref = mc;
+                tc_fence_before();
+                if (t == 0) asm volatile("bar.arrive 1, 256;" ::: "memory");
+                else        asm volatile("bar.arrive 2, 256;" ::: "memory");
+            } else {
+                if (t == 0) asm volatile("bar.sync 1, 256;" ::: "memory");
+                else        asm volatile("bar.sync 2, 256;" ::: "memory");
+                tc_fence_after();
+                mc = *mref;
+            }
+            if (j > 0) {
+                // the P_t buffer and O_t belong to the tensor core until PV of tile j-1 has retired
+                mbar_wait(bar_pv_done + 8 * t, (uint32_t)(j - 1) & 1u);
+                if (releaser) {                                  // PV(t, j-1) has retired: this tile is done with V_{j-1}
+                    if (elect_one()) mbar_arrive(bar_empty + 8 * ((2 * j - 1) % kRing));
+                    __syncwarp();
+                }
+                tc_fence_after();
+                if (rescale) {
+#pragma unroll
+                    for (int ch = 0; ch < kOCols / 16; ++ch) {
+                        uint32_t r[16];
+                        tmem_ld_32x32b_x16(tO + ch * 16, r);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) r[e] = __float_as_uint(__uint_as_float(r[e]) * alpha);
+                        tmem_st_32x32b_x16(tO + ch * 16, r);
+                    }
+                    tmem_st_wait();
+                }
+            }
+            // this thread's 64 keys: two 32-score chunks -> packed fp16 -> its half of the P tile (K-major, SWIZZLE_128B)
+            {
+                uint32_t ra[32], rb[32];
+                uint8_t* dst = pP + hf * kTileBytes;
+                tmem_ld_32x32b_x32(tS + hf * 64, ra);
+                tmem_ld_wait();
+                tmem_ld_32x32b_x32(tS + hf * 64 + 32, rb);
+                if (masked) mask_chunk(ra, hf * 64, valid);
+                exp_chunk<POLY>(ra, 0, c, mc, dst, sw);
+                tmem_ld_wait();
+                tc_fence_before();                               // last read of S_t by this thread: release it for the next QK
+                mbar_arrive(bar_s_free + 8 * t);
+                if (masked) mask_chunk(rb, hf * 64 + 32, valid);
+                exp_chunk<POLY>(rb, 1, c, mc, dst, sw);
+            }
+            fence_proxy_async_smem();
+            tc_fence_before();
+            mbar_arrive(bar_p_full + 8 * t);
+        }
+        // ---- epilogue: O / l -> fp16 -> smem (SW128, first half of this tile's P buffer) -> TMA store; 32 columns per thread
+        mbar_wait(bar_pv_done + 8 * t, (uint32_t)(nkv - 1) & 1u);
+        tc_fence_after();
+        float inv;
+        {
+            uint32_t r[16];
+            tmem_ld_32x32b_x16(tO + 64, r);
+            tmem_ld_wait();
+            inv = 1.f / __uint_as_float(r[0]);
+        }
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch) {
+            uint32_t r[16];
+            tmem_ld_32x32b_x16(tO + (hf * 2 + ch) * 16, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int v8 = 0; v8 < 2; ++v8) {
+                uint4 u;
+                __half2* hh = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    hh[e] = __floats2half2_rn(__uint_as_float(r[v8 * 8 + 2 * e]) * inv, __uint_as_float(r[v8 * 8 + 2 * e + 1]) * inv);
+                const uint32_t chunk16 = (uint32_t)((hf * 2 + ch) * 2 + v8);
+                *reinterpret_cast<uint4*>(pP + ((chunk16 ^ sw) << 4)) = u;
+            }
+        }
+        fence_proxy_async_smem();
+        if (t == 0) asm volatile("bar.sync 3, 256;" ::: "memory");
+        else        asm volatile("bar.sync 4, 256;" ::: "memory");
+        if (releaser && lane == 0) {
+            asm volatile(
+                "cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
+                ::"l"(reinterpret_cast<uint64_t>(&tm_out)), "r"(sP + t * 2 * kTileBytes), "r"(head * kD), "r"(q0 + t * kQ), "r"(img) : "memory");
+            tma_store_commit();
+            tma_store_wait_all<0>();
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        tc_fence_after();
+        tmem_dealloc(tmem_base, kTmemCols);
+    }
+}
+
 }  // namespace wiw
 
 using namespace wiw;
@@ -1932,13 +2222,16 @@ extern "C" int wiw_attention_spatial(const void* qkv, void* out, int images, int
         WIW_CHECK_CUDA(cudaFuncSetAttribute(attn_spatial_ts4_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemTS4));
         WIW_CHECK_CUDA(cudaFuncSetAttribute(attn_spatial_ss2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemSS2));
         WIW_CHECK_CUDA(cudaFuncSetAttribute(attn_spatial_ss2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemSS2));
+        WIW_CHECK_CUDA(cudaFuncSetAttribute(attn_spatial_ss3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemSS2));
     }
     // development switches for same-box A/B runs: WIW_ATTN_TS=0 -> the shared-memory-operand kernel; WIW_ATTN_POLY = exponential
     // pairs (of every 4) evaluated on the FMA pipe instead of MUFU (see exp2_poly)
-    static const int ts = getenv("WIW_ATTN_TS") ? atoi(getenv("WIW_ATTN_TS")) : 5;        // 0 = SS kernel, 1 = TS 8 softmax warps, 2 = TS 16, 3 = TS 16 + double-buffered 64-key scores
+    static const int ts = getenv("WIW_ATTN_TS") ? atoi(getenv("WIW_ATTN_TS")) : 6;        // 0 = SS kernel, 1 = TS 8 softmax warps, 2 = TS 16, 3 = TS 16 + double-buffered 64-key scores
     static const int poly = getenv("WIW_ATTN_POLY") ? atoi(getenv("WIW_ATTN_POLY")) : 1;
     dim3 grid((S + 2 * kQ - 1) / (2 * kQ), C / 64, images);
-    if (ts == 5) {
+    if (ts == 6) {
+        attn_spatial_ss3_kernel<1><<<grid, kAttnThreads3, kAttnSmemSS2, stream>>>(tm_qkv, tm_out, a, C);
+    } else if (ts == 5) {
         if (poly == 2) attn_spatial_ss2_kernel<2><<<grid, kAttnThreads2, kAttnSmemSS2, stream>>>(tm_qkv, tm_out, a, C);
         else attn_spatial_ss2_kernel<1><<<grid, kAttnThreads2, kAttnSmemSS2, stream>>>(tm_qkv, tm_out, a, C);
     } else if (ts == 4) {
