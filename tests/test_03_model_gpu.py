@@ -144,3 +144,46 @@ def test_scheduler_index_arithmetic_bit_exact(golden_dir):
         assert s.sigmas.numpy().tobytes() == g[f"sigmas_{n}"].tobytes()
         assert s.timesteps.numpy().tobytes() == g[f"timesteps_{n}"].tobytes()
         assert [s.index_for_timestep(t) for t in s.timesteps] == list(range(n))
+
+
+# ----------------------------------------------------------------------------- conditioning front-end on the sm_100a kernels
+def test_vae_encoder_engine_vs_reference_golden(golden_dir):
+    """engine.VAEEncoderEngine (SD-VAE encoder + quant_conv on the implicit-GEMM / GroupNorm / attention kernels, fp16 storage,
+    fp32 accumulation) against the reference's own fp32 `vae.encode(x).latent_dist.mode()` (tests/golden/frontend_tiny.npz).
+    Tolerance: the reference runs this stage in fp32 (force_upcast); fp16 storage between ~25 layers -> relative RMS <= 1e-2 and
+    PSNR >= 45 dB on the latent range."""
+    from wiw_b200.engine import VAEEncoderEngine
+    from wiw_b200.frontend import vae_encoder_param_spec
+    g = np.load(os.path.join(golden_dir, "frontend_tiny.npz"))
+    c = TINY_VAE
+    esd = W.random_init(vae_encoder_param_spec(c.block_out_channels, c.layers_per_block, c.latent_channels), SEED_VAE + 1)
+    enc = VAEEncoderEngine(c, esd, DEV)
+    got = enc.encode_mode(torch.from_numpy(g["image"])).float().cpu()
+    ref = torch.from_numpy(g["latent_mode"])
+    torch.cuda.synchronize()
+    assert got.shape == ref.shape and torch.isfinite(got).all()
+    r, p = rel_rms(got, ref), psnr_range(got, ref)
+    from conftest import record_parity
+    record_parity("vae_encoder_engine_tiny_vs_reference_fp32", rel_rms=r, psnr_db=p)
+    assert r < 1e-2 and p > 45.0, (r, p)
+
+
+def test_vae_encoder_engine_full_size_vs_fp32_path():
+    """Same engine at the deployed size (576x1024 px, full SD-VAE encoder) against the fp32 PyTorch path the worker uses by
+    default (frontend.vae_encode_mode = the reference's arithmetic, checked against the golden on the CPU)."""
+    from wiw_b200.config import FULL_VAE
+    from wiw_b200.engine import VAEEncoderEngine
+    from wiw_b200.frontend import vae_encode_mode, vae_encoder_param_spec
+    c = FULL_VAE
+    esd = W.random_init_on_device(vae_encoder_param_spec(c.block_out_channels, c.layers_per_block, c.latent_channels), 2, DEV)
+    img = torch.from_numpy(np.random.Generator(np.random.PCG64(9)).uniform(-1, 1, (1, 3, 576, 1024)).astype(np.float32)).to(DEV)
+    torch.backends.cudnn.allow_tf32 = False
+    ref = vae_encode_mode({k: v.float() for k, v in esd.items()}, img).float().cpu()
+    torch.backends.cudnn.allow_tf32 = True
+    got = VAEEncoderEngine(c, esd, DEV).encode_mode(img).float().cpu()
+    torch.cuda.synchronize()
+    assert got.shape == (1, 4, 72, 128) and torch.isfinite(got).all()
+    r, p = rel_rms(got, ref), psnr_range(got, ref)
+    from conftest import record_parity
+    record_parity("vae_encoder_engine_full_size_vs_fp32_path", rel_rms=r, psnr_db=p)
+    assert r < 1e-2 and p > 45.0, (r, p)
