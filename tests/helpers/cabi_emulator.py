@@ -189,6 +189,24 @@ class FakeLib:
         return 0
 
 
+    def wiw_resize_bicubic_u8(self, src, tmp, dst, planes, H, W, oh, ow, bounds_h, kk_h, ksize_h, bounds_v, kk_v, ksize_v, lut, stream):
+        """Pillow's integer two-pass resampler from the host-built tables (22-bit fixed point, 8-bit intermediate), then the LUT."""
+        x = self._t(src, (planes, H, W), np.uint8).astype(np.int64)
+        bh, kh = self._t(bounds_h, (ow, 2), np.int32), self._t(kk_h, (ow, ksize_h), np.int32).astype(np.int64)
+        bv, kv = self._t(bounds_v, (oh, 2), np.int32), self._t(kk_v, (oh, ksize_v), np.int32).astype(np.int64)
+        t = np.zeros((planes, H, ow), np.int64)
+        for xx in range(ow):
+            x0, n = int(bh[xx, 0]), int(bh[xx, 1])
+            t[:, :, xx] = np.clip(((x[:, :, x0:x0 + n] * kh[xx, :n]).sum(-1) + (1 << 21)) >> 22, 0, 255)
+        self._t(tmp, (planes, H, ow), np.uint8)[...] = t.astype(np.uint8)
+        o = np.zeros((planes, oh, ow), np.int64)
+        for yy in range(oh):
+            y0, n = int(bv[yy, 0]), int(bv[yy, 1])
+            o[:, yy, :] = np.clip(((t[:, y0:y0 + n, :] * kv[yy, :n, None]).sum(1) + (1 << 21)) >> 22, 0, 255)
+        self._t(dst, (planes, oh, ow), np.uint8)[...] = self._t(lut, (256,), np.uint8)[o]
+        return 0
+
+
 def install(monkeypatch):
     """Route wiw_b200.lib / ops to a FakeLib for the duration of one test (CPU tensors, no streams)."""
     from wiw_b200 import lib as L

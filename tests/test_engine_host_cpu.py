@@ -71,3 +71,77 @@ def test_rollout_and_decode_sequencing_vs_reference_pipeline(emu, golden_dir):
     frames = (f32 / 2 + 0.5).clamp(0, 1).numpy()
     assert O.psnr(frames, g["frames"][0]) >= 45.0
     assert O.psnr(u8.numpy().astype(np.float32) / 255.0, g["frames"][0]) >= 45.0
+
+
+def test_vae_encoder_sequencing_vs_golden(emu, golden_dir):
+    """the SD-VAE encoder + quant_conv on the implicit-GEMM / GroupNorm wrappers reproduces the
+    reference's fp32 posterior mean (frontend_tiny.npz) -- asymmetric stride-2 taps, shortcut convs, single-head attention and
+    the quant_conv fold."""
+    from wiw_b200.engine import VAEEncoderEngine
+    from wiw_b200.frontend import vae_encoder_param_spec
+    g = np.load(os.path.join(golden_dir, "frontend_tiny.npz"))
+    c = TINY_VAE
+    esd = W.random_init(vae_encoder_param_spec(c.block_out_channels, c.layers_per_block, c.latent_channels), 13)
+    enc = VAEEncoderEngine(c, esd, "cpu")
+    got = enc.encode_mode(torch.from_numpy(g["image"])).float()
+    ref = torch.from_numpy(g["latent_mode"])
+    assert got.shape == ref.shape
+    assert rel_rms(got, ref) < 1e-2, rel_rms(got, ref)
+
+
+def test_worker_request_path_on_host(emu, tmp_path):
+    """Request dict -> response dict through the real WorldModelWorker / Navigator / Rollout / resizer on CPU tensors (C ABI
+    emulated): shapes, dtypes, determinism of the seeded generator, and the resize stage being byte-identical to the reference's
+    own post-processing (PIL BICUBIC + to_tensor + (clip*255).astype(uint8), api_models/__init__.py:159-166,229)."""
+    from transformers import CLIPVisionConfig, CLIPVisionModelWithProjection
+    from wiw_b200 import wm_worker as WW
+    from wiw_b200.frontend import vae_encoder_param_spec
+    args = WW.build_parser().parse_args(["--width", "128", "--height", "64", "--out_width", "48", "--out_height", "40", "--num_frames", "8",
+                                         "--action_input_channel", "8", "--num_inference_steps", "2", "--device", "cpu"])
+    unet = UNetEngine(TINY_UNET, W.random_init(W.unet_param_spec(TINY_UNET), 11), "cpu")
+    vae = VAEDecoderEngine(TINY_VAE, W.random_init(W.vae_decoder_param_spec(TINY_VAE), 12), "cpu")
+    c = TINY_VAE
+    esd = W.random_init(vae_encoder_param_spec(c.block_out_channels, c.layers_per_block, c.latent_channels), 13)
+    torch.manual_seed(3)
+    clip = CLIPVisionModelWithProjection(CLIPVisionConfig(hidden_size=64, intermediate_size=128, num_hidden_layers=1, num_attention_heads=2,
+                                                          patch_size=32, projection_dim=TINY_UNET.cross_attention_dim)).eval()
+    nav = WW.Navigator(args, Rollout(unet, vae, "cpu", use_cuda_graph=False), clip, esd, "cpu")
+    worker = WW.WorldModelWorker(args, nav)
+    rng = np.random.default_rng(0)
+    req = {"b_action": np.array([[4, 1, 2, 2, 1, 3, 1, 1]], dtype=np.int64), "b_image": rng.integers(0, 256, size=(1, 4, 64, 128), dtype=np.uint8),
+           "save_dirs": [str(tmp_path / "a")], "request_model_name": "igen", "return_objects": [True]}
+    nav.generator.manual_seed(1)
+    out = worker.do_some_tasks(req)
+    WW.check_outputdict(out)
+    pf = out["pred_frames"]
+    assert pf.shape == (1, 8, 3, 40, 48) and pf.dtype == np.uint8 and pf.std() > 1.0
+    nav.generator.manual_seed(1)
+    full = nav.inference(WW.action_ids_idx_encode(req["b_action"]), req["b_image"])          # uint8 [1, 8, 3, 64, 128]
+    ref = (np.clip(WW.images_to_tensor(full, save_size=(48, 40)).numpy(), 0, 1) * 255).astype(np.uint8)
+    assert np.array_equal(pf, ref)
+
+
+def test_files_mode_writes_reference_bytes(emu, tmp_path):
+    """Files mode (<save_dir>/<idx>.jpg + action_seq.json): the JPEGs written from the device-side resize equal the ones the
+    reference's images_to_tensor -> save_predict chain writes from the same full-resolution frames."""
+    from wiw_b200 import wm_worker as WW
+
+    class Nav:                                             # fixed full-resolution frames: isolates the output stage
+        device = torch.device("cpu")
+
+        def inference(self, actions, images_u8, ow=None, oh=None, on_device=False, **kw):
+            g = torch.Generator().manual_seed(5)
+            return torch.randint(0, 256, (actions.shape[0], 8, 3, 64, 128), generator=g, dtype=torch.uint8)
+
+    args = WW.build_parser().parse_args(["--width", "128", "--height", "64", "--out_width", "48", "--out_height", "40", "--num_frames", "8"])
+    worker = WW.WorldModelWorker(args, Nav())
+    acts = np.array([[4, 1, 2, 2, 1, 3, 1, 1]], dtype=np.int64)
+    req = {"b_action": acts, "b_image": np.zeros((1, 3, 64, 128), np.uint8), "save_dirs": [str(tmp_path / "new")], "request_model_name": "igen"}
+    out = worker.do_some_tasks(req)
+    assert out == {"save_dirs": req["save_dirs"]}
+    full = Nav().inference(torch.zeros(1, 8, 8), None).numpy()
+    WW.save_predict(WW.images_to_tensor(full, save_size=(48, 40)).numpy(), acts, [str(tmp_path / "ref")])
+    names = sorted(os.listdir(tmp_path / "ref"))
+    assert names == sorted(os.listdir(tmp_path / "new")) and len(names) == 9
+    for n in names:
+        assert open(tmp_path / "ref" / n, "rb").read() == open(tmp_path / "new" / n, "rb").read(), n

@@ -105,3 +105,14 @@ def test_tconv3_frame_taps_and_blend(fake, b_, f, s, c):
     ref = 0.3 * (ref + tab.float().view(b_, f, 1, c)) + res.float()
     close(y, ref)
     assert fake.calls[-1][:2] == ops._tbox(s, f)
+
+
+@pytest.mark.parametrize("n,h,w,c,cout", [(2, 8, 16, 64, 64), (1, 18, 32, 64, 32)])
+def test_conv3x3_stride2_asymmetric_padding(fake, n, h, w, c, cout):
+    """The VAE encoder's downsampler: F.pad(x, (0, 1, 0, 1)) then a stride-2 conv without padding (downsampling.py)."""
+    x = rnd(n, h, w, c, seed=1).half()
+    wt, b = rnd(cout, c, 3, 3, seed=2, scale=(9 * c) ** -0.5), rnd(cout, seed=3)
+    y = ops.conv3x3_s2(x, ops.prep_conv(wt, b, "cpu"), asym=True)
+    xp = F.pad(x.float().permute(0, 3, 1, 2), (0, 1, 0, 1))
+    ref = F.conv2d(xp, wt.half().float(), b, stride=2).permute(0, 2, 3, 1)
+    close(y[..., :cout], ref)

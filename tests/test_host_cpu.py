@@ -120,3 +120,19 @@ def test_pair_layout_for_cfg_split():
     assert sharding.pair_branch_indices(3, 5, 8) == [2] and sharding.pair_branch_indices(3, 7, 8) == []
     pairs, owner = sharding.pair_layout(5, 4)
     assert owner == [(0, 0), (2, 0), (0, 1), (2, 1), (0, 2)] and sharding.pair_branch_indices(5, 3, 4) == [1, 3]
+
+
+def test_library_contains_native_tcgen05_and_tma_code():
+    """The built library is native sm_100a code: its SASS holds the tensor-core (UTCHMMA, incl. the 2-CTA form), TMEM (LDTM / STTM)
+    and TMA (UTMALDG / UTMASTG) instructions the hot kernels are written around (mnemonics: B200_PROFILING.md)."""
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([cuobjdump, "-sass", L.LIB_PATH], capture_output=True, text=True, timeout=300).stdout
+    assert "sm_100a" in sass or "SM100" in sass.upper()
+    for mnemonic in ("UTCHMMA", "UTCHMMA.2CTA", "LDTM", "STTM", "UTMALDG.5D", "UTMALDG.5D.2CTA", "UTMASTG.4D", "UTCBAR"):
+        assert mnemonic in sass, f"{mnemonic} missing from the library's SASS"
+    for kernel in ("conv_gemm_kernel", "attn_spatial_kernel", "temporal_attn_mma_kernel", "layernorm_lpr_kernel", "gn_apply_kernel"):
+        assert kernel in sass

@@ -141,6 +141,29 @@ class _Common:
         return out.view(n, h, w, c)
 
 
+    # ---- single-head (d = C) spatial attention with GroupNorm and residual (VAE mid blocks, unet_3d_blocks.py:958-969 /
+    #      unet_2d_blocks.py UNetMidBlock2D): scores and P@V run on the implicit-GEMM kernel, one image at a time
+    def single_head_attention(self, x: torch.Tensor, norm: ops.NormWeight, wq: ops.GemmWeight, wk: ops.GemmWeight,
+                              wv: ops.GemmWeight, wo: ops.GemmWeight) -> torch.Tensor:
+        n, h, w, c = x.shape
+        S = h * w
+        if S % 64:
+            raise ValueError("VAE attention needs h*w % 64 == 0")
+        g = ops.group_norm(x, norm, n, 1e-6, False).view(n * S, c)
+        q, k, v = ops.linear(g, wq), ops.linear(g, wk), ops.linear(g, wv)
+        vt = ops.transpose(v.view(n, S, c))                                   # [n, c, S]
+        o = torch.empty(n * S, c, dtype=torch.float16, device=x.device)
+        scores = torch.empty(S, S, dtype=torch.float16, device=x.device)
+        for f in range(n):
+            kf = ops.GemmWeight(w=k[f * S:(f + 1) * S], bias=None, n=S, k=c, cin=c, taps=1, bn=ops.pick_bn(S), n_real=S)
+            ops.linear(q[f * S:(f + 1) * S], kf, out=scores)
+            ops.softmax_rows_(scores, c ** -0.5)
+            vf = ops.GemmWeight(w=vt[f], bias=None, n=c, k=S, cin=S, taps=1, bn=ops.pick_bn(c), n_real=c)
+            ops.linear(scores, vf, out=o[f * S:(f + 1) * S])
+        out = ops.linear(o, wo, res=x.view(n * S, c))
+        return out.view(n, h, w, c)
+
+
 # =========================================================================== UNet
 class UNetEngine(_Common):
     """The spatio-temporal UNet of the SVD-dagger world model (micro_cond action strategy)."""
@@ -391,25 +414,7 @@ class VAEDecoderEngine(_Common):
         self.tco_b = sd["time_conv_out.bias"].float().contiguous().to(self.device)
 
     def attention(self, x: torch.Tensor) -> torch.Tensor:
-        """Single-head (d = C) spatial attention with GroupNorm and residual (unet_3d_blocks.py:958-969):
-        scores and P@V run on the implicit-GEMM kernel, one frame at a time."""
-        n, h, w, c = x.shape
-        S = h * w
-        if S % 64:
-            raise ValueError("VAE attention needs h*w % 64 == 0")
-        g = ops.group_norm(x, self.a_norm, n, 1e-6, False).view(n * S, c)
-        q, k, v = ops.linear(g, self.a_q), ops.linear(g, self.a_k), ops.linear(g, self.a_v)
-        vt = ops.transpose(v.view(n, S, c))                                   # [n, c, S]
-        o = torch.empty(n * S, c, dtype=torch.float16, device=x.device)
-        scores = torch.empty(S, S, dtype=torch.float16, device=x.device)
-        for f in range(n):
-            kf = ops.GemmWeight(w=k[f * S:(f + 1) * S], bias=None, n=S, k=c, cin=c, taps=1, bn=ops.pick_bn(S), n_real=S)
-            ops.linear(q[f * S:(f + 1) * S], kf, out=scores)
-            ops.softmax_rows_(scores, c ** -0.5)
-            vf = ops.GemmWeight(w=vt[f], bias=None, n=c, k=S, cin=S, taps=1, bn=ops.pick_bn(c), n_real=c)
-            ops.linear(scores, vf, out=o[f * S:(f + 1) * S])
-        out = ops.linear(o, self.a_out, res=x.view(n * S, c))
-        return out.view(n, h, w, c)
+        return self.single_head_attention(x, self.a_norm, self.a_q, self.a_k, self.a_v, self.a_out)
 
     def decode(self, z: torch.Tensor, num_frames: int, out_u8: Optional[torch.Tensor] = None,
                out_f32: Optional[torch.Tensor] = None) -> None:
@@ -437,3 +442,71 @@ class VAEDecoderEngine(_Common):
                                        out_u8[b * F:(b + 1) * F].data_ptr() if out_u8 is not None else None,
                                        out_f32[b * F:(b + 1) * F].data_ptr() if out_f32 is not None else None,
                                        F, H * W, cs, L.stream_ptr()))
+
+
+# =========================================================================== SD-VAE encoder (conditioning frame)
+class VAEEncoderEngine(_Common):
+    """`AutoencoderKLTemporalDecoder.encode(x).latent_dist.mode()` on the sm_100a kernels: the SD VAE Encoder
+    (DP/models/autoencoders/vae.py:47-182; DownEncoderBlock2D / UNetMidBlock2D in DP/models/unets/unet_2d_blocks.py) followed by
+    quant_conv (autoencoder_kl_temporal_decoder.py:316-341), posterior mean only.  `sd` holds `encoder.*` and `quant_conv.*`.
+
+    OPT-IN (`wm_worker --own_vae_encoder`): the reference runs this stage in fp32 (`force_upcast`), here activations are fp16
+    with fp32 accumulation like the rest of the path.  Host logic is checked on the CPU against the reference golden
+    (tests/test_engine_host_cpu.py); it is not the default until it has been measured on a real checkpoint."""
+
+    def __init__(self, cfg: VAEConfig, sd: SD, device="cuda"):
+        super().__init__(device)
+        cfg.validate()
+        self.cfg = cfg
+        boc = cfg.block_out_channels
+        self.conv_in = self._conv(sd, "encoder.conv_in")
+        self.down: List[List[dict]] = []
+        self.down_conv: Dict[int, ops.GemmWeight] = {}
+        for i in range(len(boc)):
+            self.down.append([self._res2d(sd, f"encoder.down_blocks.{i}.resnets.{j}") for j in range(cfg.layers_per_block)])
+            if i < len(boc) - 1:
+                self.down_conv[i] = self._conv(sd, f"encoder.down_blocks.{i}.downsamplers.0.conv")
+        self.mid0 = self._res2d(sd, "encoder.mid_block.resnets.0")
+        self.mid1 = self._res2d(sd, "encoder.mid_block.resnets.1")
+        a = "encoder.mid_block.attentions.0"
+        self.a_norm = self._norm(sd, a + ".group_norm")
+        self.a_q, self.a_k, self.a_v = self._lin(sd, a + ".to_q"), self._lin(sd, a + ".to_k"), self._lin(sd, a + ".to_v")
+        self.a_out = self._lin(sd, a + ".to_out.0")
+        self.norm_out = self._norm(sd, "encoder.conv_norm_out")
+        # quant_conv (1x1, 2L -> 2L) folded into conv_out in fp32 at load time: Wq @ W_out, Wq @ b_out + bq (exact algebra, one launch less)
+        wq = sd["quant_conv.weight"].float().flatten(1)                                        # [2L, 2L]
+        w_out, b_out = sd["encoder.conv_out.weight"].float(), sd["encoder.conv_out.bias"].float()
+        w_fused = torch.einsum("om,mikl->oikl", wq, w_out)
+        b_fused = wq @ b_out + sd["quant_conv.bias"].float()
+        self.conv_out = ops.prep_conv(w_fused, b_fused, self.device)
+        self.latent_channels = cfg.latent_channels
+
+    def _res2d(self, sd: SD, p: str) -> dict:
+        sc = self._conv(sd, p + ".conv_shortcut") if (p + ".conv_shortcut.weight") in sd else None
+        return dict(norm1=self._norm(sd, p + ".norm1"), conv1=self._conv(sd, p + ".conv1"), norm2=self._norm(sd, p + ".norm2"),
+                    conv2=self._conv(sd, p + ".conv2"), shortcut=sc)
+
+    def _resblock2d(self, x: torch.Tensor, r: dict) -> torch.Tensor:
+        n = x.shape[0]
+        a = ops.group_norm(x, r["norm1"], n, 1e-6, True)
+        hdn = ops.conv3x3(a, r["conv1"])
+        a = ops.group_norm(hdn, r["norm2"], n, 1e-6, True)
+        sc = x if r["shortcut"] is None else ops.conv1x1(x, r["shortcut"])
+        return ops.conv3x3(a, r["conv2"], res=sc)
+
+    @torch.no_grad()
+    def encode_mode(self, image: torch.Tensor) -> torch.Tensor:
+        """image float [B, 3, H, W] in [-1, 1] (H, W multiples of 8) -> posterior mean fp16 [B, L, H/8, W/8] (not scaled)."""
+        x = ops.nchw_to_nhwc(image.to(self.device, torch.float16).contiguous(), 64)            # 3 real channels, zero-padded to 64
+        x = ops.conv3x3(x, self.conv_in)
+        for i, blocks in enumerate(self.down):
+            for r in blocks:
+                x = self._resblock2d(x, r)
+            if i in self.down_conv:
+                x = ops.conv3x3_s2(x, self.down_conv[i], asym=True)
+        x = self._resblock2d(x, self.mid0)
+        x = self.single_head_attention(x, self.a_norm, self.a_q, self.a_k, self.a_v, self.a_out)
+        x = self._resblock2d(x, self.mid1)
+        x = ops.group_norm(x, self.norm_out, x.shape[0], 1e-6, True)
+        moments = ops.conv3x3(x, self.conv_out)                                                 # [B, h, w, 32] (2L real channels)
+        return ops.nhwc_to_nchw(moments, self.latent_channels)

@@ -228,9 +228,11 @@ def conv1x1(x: torch.Tensor, gw: GemmWeight, out: Optional[torch.Tensor] = None)
     return y.view(n, h, w, gw.n)
 
 
-def conv3x3_s2(x: torch.Tensor, gw: GemmWeight, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+def conv3x3_s2(x: torch.Tensor, gw: GemmWeight, out: Optional[torch.Tensor] = None, asym: bool = False) -> torch.Tensor:
     """Conv2d 3x3 stride 2 pad 1 (Downsample2D, downsampling.py:69-146) through a space-to-depth view:
-    input pixel (2Y+py, 2X+px) -> coords (c + px*C, X, py, Y, n); tap d=-1 reads parity 1 at X-1 / Y-1."""
+    input pixel (2Y+py, 2X+px) -> coords (c + px*C, X, py, Y, n); tap d=-1 reads parity 1 at X-1 / Y-1.
+    asym=True: the VAE encoder's variant (downsampling.py `padding == 0` branch: F.pad(x, (0,1,0,1)) then stride 2 without
+    padding), i.e. taps at rows 2Y, 2Y+1, 2Y+2 -- the row / column past the image is the tensor map's zero fill."""
     _chk(x)
     n, h, w, c = x.shape
     assert c == gw.cin and gw.taps == 9 and h % 2 == 0 and w % 2 == 0
@@ -239,8 +241,8 @@ def conv3x3_s2(x: torch.Tensor, gw: GemmWeight, out: Optional[torch.Tensor] = No
         out = torch.empty(n, ho, wo, gw.n, dtype=torch.float16, device=x.device)
     bx, by, bz = _box3(wo, ho, n)
 
-    def par(d):           # filter offset d-1 in {-1,0,1} -> (parity, coarse offset)
-        return [(1, -1), (0, 0), (1, 0)][d]
+    def par(d):           # filter tap d in {0,1,2} -> (parity, coarse offset); symmetric padding: rows 2Y-1, 2Y, 2Y+1
+        return [(0, 0), (1, 0), (0, 1)][d] if asym else [(1, -1), (0, 0), (1, 0)][d]
 
     taps = []
     for ky in range(3):

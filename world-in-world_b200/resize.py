@@ -95,7 +95,7 @@ class GpuResizer:
         from . import lib as L
         lib = L.require_device()
         H, W, oh, ow = self.shape
-        assert planes.dtype == torch.uint8 and planes.is_cuda and planes.is_contiguous() and planes.shape[-2:] == (H, W)
+        assert planes.dtype == torch.uint8 and planes.device == self.device and planes.is_contiguous() and planes.shape[-2:] == (H, W)
         P = planes.numel() // (H * W)
         tmp = torch.empty(P, H, ow, dtype=torch.uint8, device=self.device)
         out = torch.empty(*planes.shape[:-2], oh, ow, dtype=torch.uint8, device=self.device)

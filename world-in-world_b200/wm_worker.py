@@ -198,6 +198,7 @@ class Navigator:
         self.device = torch.device(device)
         self.generator = torch.Generator(device=self.device).manual_seed(1)        # eval_inference.py:97
         self.num_inference_steps = getattr(args, "num_inference_steps", 30)        # eval_inference.py:255 hard-codes 30
+        self.vae_enc = None             # optional engine.VAEEncoderEngine (--own_vae_encoder); default: PyTorch fp32 path like the reference
         self.noise_aug_strength = 0.02
 
     @torch.no_grad()
@@ -226,7 +227,10 @@ class Navigator:
             noise = torch.stack([torch.randn(pre.shape[1:], generator=g, device=dev, dtype=pre.dtype) for g in gens])
         else:
             noise = torch.randn(pre.shape, generator=self.generator, device=dev, dtype=pre.dtype)   # pipeline :521-523
-        image_latents = frontend.vae_encode_mode(self.vae_encoder_sd, pre + self.noise_aug_strength * noise).to(torch.float16)
+        if self.vae_enc is not None:
+            image_latents = self.vae_enc.encode_mode(pre + self.noise_aug_strength * noise)
+        else:
+            image_latents = frontend.vae_encode_mode(self.vae_encoder_sd, pre + self.noise_aug_strength * noise).to(torch.float16)
         if latents is None and seeds is not None:
             raw = torch.stack([torch.randn((F, 4, H // 8, W // 8), generator=g, device=dev, dtype=torch.float16) for g in gens])
             diag = torch.diagonal(actions, dim1=-2, dim2=-1)
@@ -282,8 +286,9 @@ class WorldModelWorker:
             if return_objects:
                 # only the 480x480 uint8 result crosses PCIe
                 return {"pred_frames": self.resized_frames(frames).cpu().numpy(), "save_dirs": save_dirs}
-            video = images_to_tensor(frames.cpu().numpy(), save_size=(self.args.out_width, self.args.out_height)).numpy()
-            save_predict(video, b_action, save_dirs)
+            # files mode (saver.py:221-274): same device-side resize + requantisation, the JPEGs hold exactly the bytes the reference's
+            # images_to_tensor -> save_predict chain would write
+            save_predict_u8(self.resized_frames(frames).cpu().numpy(), b_action, save_dirs)
             return {"save_dirs": save_dirs}
         except Exception:                       # never die inside task_fn (SURVEY.md 8b "Errors")
             traceback.print_exc()
@@ -415,6 +420,9 @@ def build_parser() -> argparse.ArgumentParser:
     p.add_argument("--gpus", type=int, default=1)
     p.add_argument("--rank", type=int, default=0)
     p.add_argument("--master_port", type=int, default=0)
+    p.add_argument("--own_vae_encoder", action="store_true",
+                   help="run the conditioning frame's VAE encode on the sm_100a kernels in fp16 (opt-in; the reference and the "
+                        "default path run it in fp32 on PyTorch library kernels)")
     p.add_argument("--cfg_split", action="store_true",
                    help="with --gpus R: requests of at most R/2 branches run each branch on a pair of GPUs (one CFG row each)")
     return p
@@ -462,6 +470,9 @@ def build_worker(args) -> WorldModelWorker:
     rollout = Rollout(UNetEngine(ucfg, usd, dev), VAEDecoderEngine(vcfg, vsd, dev), dev)
     del usd, vsd
     nav = Navigator(args, rollout, clip, esd, dev)
+    if getattr(args, "own_vae_encoder", False):
+        from .engine import VAEEncoderEngine
+        nav.vae_enc = VAEEncoderEngine(vcfg, esd, dev)
     if getattr(args, "gpus", 1) > 1:
         return ShardedWorldModelWorker(args, nav, args.rank, args.gpus)
     return WorldModelWorker(args, nav)
