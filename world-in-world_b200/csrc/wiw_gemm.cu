@@ -74,7 +74,7 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmArgs& g, int tile, in
     return t;
 }
 
-template <int CG, int GEGLU>      // GEGLU: 0 = plain epilogue, 1 = GEGLU with the A&S erf (gelu_fast_f), 2 = GEGLU with the tanh-fit erf
+template <int CG, int GEGLU>      // GEGLU: 0 = plain epilogue, 1 = GEGLU with the A&S erf (gelu_fast_f), 2 = GEGLU with the tanh-fit erf, 3 = the same on packed halves (experimental)
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                  const __grid_constant__ CUtensorMap tm_out /* box = one warp's 32 rows x 32 channels */,
@@ -315,6 +315,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             for (int j = grp; j < chunks; j += 2) {
                 float v[kEpiCols];
                 uint32_t rg[kEpiCols];                              // gate half of a GEGLU tile
+                uint32_t vh[kEpiCols / 2];                          // GEGLU mode 3: the chunk's results as packed halves
                 const int half_n = g.bn >> 1;
                 {
                     // Global loads of bias / table rows are issued BEFORE tcgen05.wait::ld so their latency overlaps the
@@ -367,7 +368,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                     tmem_ld_wait();
 #pragma unroll
                     for (int c = 0; c < kEpiCols; c += 4) {
-                        if (GEGLU == 2) {
+                        if (GEGLU == 3) {
+                            vh[c / 2] = mul_gelu_tanhfit_h2(v[c], v[c + 1], __uint_as_float(rg[c]) + b4[c / 4].x, __uint_as_float(rg[c + 1]) + b4[c / 4].y);
+                            vh[c / 2 + 1] = mul_gelu_tanhfit_h2(v[c + 2], v[c + 3], __uint_as_float(rg[c + 2]) + b4[c / 4].z, __uint_as_float(rg[c + 3]) + b4[c / 4].w);
+                        } else if (GEGLU == 2) {
                             v[c] = mul_gelu_tanhfit_f(v[c], __uint_as_float(rg[c]) + b4[c / 4].x);
                             v[c + 1] = mul_gelu_tanhfit_f(v[c + 1], __uint_as_float(rg[c + 1]) + b4[c / 4].y);
                             v[c + 2] = mul_gelu_tanhfit_f(v[c + 2], __uint_as_float(rg[c + 2]) + b4[c / 4].z);
@@ -443,7 +447,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                         uint4 u;
                         __half2* h = reinterpret_cast<__half2*>(&u);
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) h[e] = __floats2half2_rn(v[c4 * 8 + 2 * e], v[c4 * 8 + 2 * e + 1]);
+                        for (int e = 0; e < 4; ++e) {
+                            if (GEGLU == 3) h[e] = *reinterpret_cast<const __half2*>(&vh[c4 * 4 + e]);
+                            else h[e] = __floats2half2_rn(v[c4 * 8 + 2 * e], v[c4 * 8 + 2 * e + 1]);
+                        }
                         *reinterpret_cast<uint4*>(p + ((uint32_t(c4) ^ sw) << 4)) = u;
                     }
                 }
@@ -524,7 +531,7 @@ static int launch_conv_gemm(const wiw_gemm_desc* d, cudaStream_t stream) {
     g.total_tiles = (int)(((m_tiles + cg - 1) / cg) * g.n_tiles);
     static const int dbg = getenv("WIW_GEMM_DBG") ? atoi(getenv("WIW_GEMM_DBG")) : 0;
     g.dbg = dbg;
-    static const int gelu_mode = getenv("WIW_GELU") ? atoi(getenv("WIW_GELU")) : 2;         // 1 = A&S erf (2 MUFU), 2 = tanh-fit erf (1 MUFU)
+    static const int gelu_mode = getenv("WIW_GELU") ? atoi(getenv("WIW_GELU")) : 2;         // 1 = A&S erf (2 MUFU), 2 = tanh-fit erf (1 MUFU), 3 = tanh-fit on packed halves (experimental)
     static const int epi = getenv("WIW_GEMM_EPI") ? atoi(getenv("WIW_GEMM_EPI")) : 1;       // development aid for A/B runs
     g.warp_store = epi ? 1 : 0;
     // one warp's 32 rows as a (pixel, row, image) box
@@ -612,12 +619,15 @@ static int launch_conv_gemm(const wiw_gemm_desc* d, cudaStream_t stream) {
         WIW_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
         WIW_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
         WIW_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+        WIW_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+        WIW_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
         attr_set = true;
     }
     if (cg == 1) {
         int grid = num_sms();
         if (grid > g.total_tiles) grid = g.total_tiles;
-        if (g.geglu && gelu_mode == 2) conv_gemm_kernel<1, 2><<<grid, kThreads, smem_bytes, stream>>>(tm_a, tm_b, tm_out, tm_res, tm_aux, g);
+        if (g.geglu && gelu_mode == 3) conv_gemm_kernel<1, 3><<<grid, kThreads, smem_bytes, stream>>>(tm_a, tm_b, tm_out, tm_res, tm_aux, g);
+        else if (g.geglu && gelu_mode == 2) conv_gemm_kernel<1, 2><<<grid, kThreads, smem_bytes, stream>>>(tm_a, tm_b, tm_out, tm_res, tm_aux, g);
         else if (g.geglu) conv_gemm_kernel<1, 1><<<grid, kThreads, smem_bytes, stream>>>(tm_a, tm_b, tm_out, tm_res, tm_aux, g);
         else conv_gemm_kernel<1, 0><<<grid, kThreads, smem_bytes, stream>>>(tm_a, tm_b, tm_out, tm_res, tm_aux, g);
     } else {
@@ -634,7 +644,8 @@ static int launch_conv_gemm(const wiw_gemm_desc* d, cudaStream_t stream) {
         attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        if (g.geglu && gelu_mode == 2) WIW_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<2, 2>, tm_a, tm_b, tm_out, tm_res, tm_aux, g));
+        if (g.geglu && gelu_mode == 3) WIW_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<2, 3>, tm_a, tm_b, tm_out, tm_res, tm_aux, g));
+        else if (g.geglu && gelu_mode == 2) WIW_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<2, 2>, tm_a, tm_b, tm_out, tm_res, tm_aux, g));
         else if (g.geglu) WIW_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<2, 1>, tm_a, tm_b, tm_out, tm_res, tm_aux, g));
         else WIW_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<2, 0>, tm_a, tm_b, tm_out, tm_res, tm_aux, g));
     }
