@@ -99,6 +99,41 @@ PROFILE = None        # set to a list to record (algorithmic flops, start event,
 
 
 _SMART_BOXES = os.environ.get("WIW_BOX3", "1") != "0"      # development aid for A/B runs: 0 = bx x by x 1 tiles only
+_WAVE_BN = os.environ.get("WIW_WAVE_BN", "1") != "0"       # development aid for A/B runs: 0 = the weight's own N-tile width always
+_FORCE_BN = int(os.environ.get("WIW_FORCE_BN", "0"))
+_SLOTS = 148                                                # SMs of a B200; CTA pairs = half
+
+
+def launch_bn(gw: "GemmWeight", m_tiles: int) -> int:
+    """N-tile width of ONE launch, chosen against wave quantisation.  The kernel is persistent with one CTA (pair) per SM
+    (pair): a launch takes ceil(tiles / slots) waves of tiles whose duration grows with bn (a cta_group::2 MMA costs bn / 2 cycles
+    for bn >= 128, profiles/r02_mma_cost_v2.txt), so the narrowest width that removes a nearly empty last wave wins:
+    the 9x16 level (35 M-tiles) runs N = 1280 as 90 pair-tiles of 256 = 2 waves on 74 pairs, but as 144 pair-tiles of 160 in the
+    same 2 waves at 62 % of the time; the 18x32 level goes from 5 waves of 256 to 7 of 160 (-12 %).  GEGLU weights are interleaved
+    per tile at load time and keep their width; the last N-tile may be ragged (its padded columns still cost a full tile)."""
+    if not _WAVE_BN or gw.geglu or gw.n < 128:
+        return gw.bn
+    if _FORCE_BN:                                                                      # development aid: measure one width everywhere
+        return min(_FORCE_BN, gw.n)
+    def cost(bn: int):
+        n_tiles = -(-gw.n // bn)
+        total = m_tiles * n_tiles
+        paired = total >= 2 * _SLOTS and not (gw.k <= 320 and gw.n <= 320)          # the library's cta_group::2 rule
+        units, slots = ((-(-m_tiles // 2)) * n_tiles, _SLOTS // 2) if paired else (total, _SLOTS)
+        waves = -(-units // slots)
+        return waves, waves * (bn + 24)                                                # + ~24 columns' worth of per-tile fixed cost
+
+    waves0, cost0 = cost(gw.bn)
+    if waves0 > 8:                                                                     # many waves: the last one hardly matters
+        return gw.bn
+    best, best_cost = gw.bn, cost0
+    for bn in (128, 160, 192, 224, 256):
+        if bn > gw.n:
+            continue
+        c = cost(bn)[1]
+        if c < 0.92 * cost0 and (c < best_cost or (c == best_cost and bn > best)):    # switch only for a clear (>= 8 %) predicted gain
+            best, best_cost = bn, c
+    return best
 
 
 def _box(width: int) -> Tuple[int, int]:
@@ -168,7 +203,8 @@ def _launch(a: torch.Tensor, a_dim, a_stride, gw: GemmWeight, out: torch.Tensor,
         d.tab_stride = int(tab.stride(0)) if tab.dim() == 2 else int(tab.shape[-1])
     d.act = int(act)
     d.s_acc, d.s_res, d.s_aux = float(s_acc), float(s_res), float(s_aux)
-    d.bx, d.by, d.bn, d.geglu = bx, by, gw.bn, int(gw.geglu)
+    m_tiles = (-(-int(out_dim[1]) // bx)) * (-(-int(out_dim[2]) // by)) * (-(-int(out_dim[3]) // bz))
+    d.bx, d.by, d.bn, d.geglu = bx, by, launch_bn(gw, m_tiles), int(gw.geglu)
     d.bz = bz
     d.num_taps, d.chunks_per_tap = len(taps), gw.cin // 64
     for i, (cb, ox, p, oy) in enumerate(taps):
@@ -183,7 +219,7 @@ def _launch(a: torch.Tensor, a_dim, a_stride, gw: GemmWeight, out: torch.Tensor,
     e1.record()
     rows = int(out_dim[1]) * int(out_dim[2]) * int(out_dim[3])
     PROFILE.append((2.0 * rows * (gw.n_real or gw.n) * (gw.k_real or gw.k), e0, e1,
-                    f"M={rows} K={gw.k} N={gw.n} taps={len(taps)} bn={gw.bn}{' geglu' if gw.geglu else ''}"
+                    f"M={rows} K={gw.k} N={gw.n} taps={len(taps)} bn={d.bn}{' geglu' if gw.geglu else ''}"
                     f"{' res' if res is not None else ''}{' aux' if aux is not None else ''}{' tab' if tab is not None else ''}"))
 
 
