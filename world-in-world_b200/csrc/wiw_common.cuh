@@ -119,11 +119,6 @@ __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* m, 
         "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
         ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(bar) : "memory");
 }
-// L2 prefetch of a tensor tile (no shared memory, no barrier): hides HBM latency for a tile the producer will load later
-__device__ __forceinline__ void tma_prefetch_l2_5d(const CUtensorMap* m, int c0, int c1, int c2, int c3, int c4) {
-    asm volatile("cp.async.bulk.prefetch.tensor.5d.L2.global.tile [%0, {%1, %2, %3, %4, %5}];"
-                 ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
-}
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, uint32_t src, int c0, int c1, int c2, int c3) {
     asm volatile(
         "cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
@@ -321,22 +316,6 @@ __device__ __forceinline__ float mul_gelu_tanhfit_f(float v, float x) {
     asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(x * p));
     const float w = v * (0.5f * x);
     return fmaf(w, t, w);
-}
-// EXPERIMENTAL (GEGLU mode 3, unmeasured): the same tanh-fit GELU on PACKED halves -- two elements per instruction:
-// 2 F2FP packs + 7 HFMA2-pipe ops + 1 tanh.approx.f16x2 per PAIR instead of 8 FMA-pipe ops + 1 MUFU per element.  The polynomial
-// and the products round to fp16 (the reference rounds value, gelu(gate) and their product to fp16 as well).
-__device__ __forceinline__ uint32_t mul_gelu_tanhfit_h2(float v0, float v1, float x0, float x1) {
-    const __half2 v = __floats2half2_rn(v0, v1), x = __floats2half2_rn(x0, x1);
-    const __half2 x2 = __hmul2(x, x);
-    __half2 p = __hfma2(x2, __float2half2_rn(-3.58549415e-4f), __float2half2_rn(3.70488970e-2f));
-    p = __hfma2(p, x2, __float2half2_rn(7.97460674e-1f));
-    const __half2 u = __hmul2(x, p);
-    uint32_t t_bits;
-    asm("tanh.approx.f16x2 %0, %1;" : "=r"(t_bits) : "r"(*reinterpret_cast<const uint32_t*>(&u)));
-    const __half2 t = *reinterpret_cast<const __half2*>(&t_bits);
-    const __half2 w = __hmul2(v, __hmul2(x, __float2half2_rn(0.5f)));
-    const __half2 o = __hfma2(w, t, w);
-    return *reinterpret_cast<const uint32_t*>(&o);
 }
 #endif  // __CUDACC__
 

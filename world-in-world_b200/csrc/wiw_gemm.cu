@@ -39,8 +39,6 @@ struct GemmArgs {
     int tab_div, tab_mod, n_total, tmem_cols;
     int tab_stride, act, out_total;
     int dbg;                                      // development aid: bit 0 = skip TMA loads, bit 1 = skip MMA issue (timing only)
-    int acc_stages, acc_stride;                   // accumulator ring in TMEM: 2 stages (default) or 3 when 3 * bn <= 512 columns (experimental)
-    int l2_prefetch;                              // > 0: the producer prefetches the A tiles of the tile `l2_prefetch` rounds ahead into L2 (1x1 layers)
     int res_slots;                                // residual (aux) chunks in flight: 8 lets a whole tile's residual prefetch behind the MMAs
     int out_bufs;                                 // staging buffers per epilogue group: 4 when no residual / aux slots compete for smem, else 2
     int warp_store;                               // 1: every epilogue warp stores its own 32-row slab (no CTA barriers); 0: one store per 128-row chunk
@@ -74,7 +72,7 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmArgs& g, int tile, in
     return t;
 }
 
-template <int CG, int GEGLU>      // GEGLU: 0 = plain epilogue, 1 = GEGLU with the A&S erf (gelu_fast_f), 2 = GEGLU with the tanh-fit erf, 3 = the same on packed halves (experimental)
+template <int CG, int GEGLU>      // GEGLU: 0 = plain epilogue, 1 = GEGLU with the A&S erf (gelu_fast_f), 2 = GEGLU with the tanh-fit erf
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                  const __grid_constant__ CUtensorMap tm_out /* box = one warp's 32 rows x 32 channels */,
@@ -93,9 +91,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     // barrier slots (8 B each)
     const uint32_t bar_full = bar_base;                         // [kMaxStages]
     const uint32_t bar_empty = bar_full + 8 * kMaxStages;       // [kMaxStages]
-    const uint32_t bar_tfull = bar_empty + 8 * kMaxStages;      // [3]
-    const uint32_t bar_tempty = bar_tfull + 24;                 // [3]
-    const uint32_t bar_rfull = bar_tempty + 24;                 // [kMaxResSlots]
+    const uint32_t bar_tfull = bar_empty + 8 * kMaxStages;      // [2]
+    const uint32_t bar_tempty = bar_tfull + 16;                 // [2]
+    const uint32_t bar_rfull = bar_tempty + 16;                 // [kMaxResSlots]
     const uint32_t bar_rempty = bar_rfull + 8 * kMaxResSlots;   // [kMaxResSlots]
     const uint32_t tmem_slot = bar_rempty + 8 * kMaxResSlots;   // uint32
     uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
@@ -119,7 +117,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             mbar_init(bar_full + 8 * i, 1);
             mbar_init(bar_empty + 8 * i, 1);
         }
-        for (int i = 0; i < 3; ++i) {
+        for (int i = 0; i < 2; ++i) {
             mbar_init(bar_tfull + 8 * i, 1);
             mbar_init(bar_tempty + 8 * i, 8 * CG);       // one arrival per epilogue warp of every CTA in the pair
         }
@@ -137,8 +135,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     if (CG == 2) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
-    const uint32_t acc_stride = (uint32_t)g.acc_stride;
-    const int acc_stages = g.acc_stages;
+    const uint32_t acc_stride = (g.bn <= 32) ? 32 : (g.bn <= 64 ? 64 : (g.bn <= 128 ? 128 : 256));
 
     if (warp == 0) {
         // ================================ TMA producer ================================
@@ -154,19 +151,6 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         for (int tile = first_tile; tile < g.total_tiles; tile += tile_step) {
             const TileCoord t = decode_tile<CG>(g, tile, cta_rank);
             const int n0 = t.n_tile * g.bn + cta_rank * (g.bn / CG);
-            if (g.l2_prefetch > 0 && g.num_taps == 1) {
-                // Small-K layers hold barely one tile in the smem ring, so a tile's loads start only ~one tile time before they are
-                // needed and the HBM latency shows.  Warm L2 with the A tile this CTA will load `l2_prefetch` rounds from now.
-                const int pt = tile + g.l2_prefetch * tile_step;
-                if (pt < g.total_tiles) {
-                    const TileCoord p = decode_tile<CG>(g, pt, cta_rank);
-                    if (elect_one()) {
-                        for (int ch = 0; ch < g.chunks_per_tap; ++ch)
-                            tma_prefetch_l2_5d(&tm_a, g.tap_cbase[0] + ch * kBlockK, p.x0 + g.tap_ox[0], g.tap_p[0], p.y0 + g.tap_oy[0], p.img);
-                    }
-                    __syncwarp();
-                }
-            }
             int kcol = 0;
             for (int tap = 0; tap < g.num_taps; ++tap) {
                 const int cb = g.tap_cbase[tap], cx = t.x0 + g.tap_ox[tap], cp = g.tap_p[tap], cy = t.y0 + g.tap_oy[tap];
@@ -239,7 +223,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                     __syncwarp();
                     if (++s == g.stages) { s = 0; ph ^= 1; }
                 }
-                if (++as == acc_stages) { as = 0; aph ^= 1; }
+                if (++as == 2) { as = 0; aph ^= 1; }
             }
             if (prof && lane == 0) { g_gemm_prof[0] = clock64() - m_t0; g_gemm_prof[1] = m_wfull; g_gemm_prof[2] = m_wacc; g_gemm_prof[3] = m_steps; }
         }
@@ -315,7 +299,6 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             for (int j = grp; j < chunks; j += 2) {
                 float v[kEpiCols];
                 uint32_t rg[kEpiCols];                              // gate half of a GEGLU tile
-                uint32_t vh[kEpiCols / 2];                          // GEGLU mode 3: the chunk's results as packed halves
                 const int half_n = g.bn >> 1;
                 {
                     // Global loads of bias / table rows are issued BEFORE tcgen05.wait::ld so their latency overlaps the
@@ -368,10 +351,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                     tmem_ld_wait();
 #pragma unroll
                     for (int c = 0; c < kEpiCols; c += 4) {
-                        if (GEGLU == 3) {
-                            vh[c / 2] = mul_gelu_tanhfit_h2(v[c], v[c + 1], __uint_as_float(rg[c]) + b4[c / 4].x, __uint_as_float(rg[c + 1]) + b4[c / 4].y);
-                            vh[c / 2 + 1] = mul_gelu_tanhfit_h2(v[c + 2], v[c + 3], __uint_as_float(rg[c + 2]) + b4[c / 4].z, __uint_as_float(rg[c + 3]) + b4[c / 4].w);
-                        } else if (GEGLU == 2) {
+                        if (GEGLU == 2) {
                             v[c] = mul_gelu_tanhfit_f(v[c], __uint_as_float(rg[c]) + b4[c / 4].x);
                             v[c + 1] = mul_gelu_tanhfit_f(v[c + 1], __uint_as_float(rg[c + 1]) + b4[c / 4].y);
                             v[c + 2] = mul_gelu_tanhfit_f(v[c + 2], __uint_as_float(rg[c + 2]) + b4[c / 4].z);
@@ -447,10 +427,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                         uint4 u;
                         __half2* h = reinterpret_cast<__half2*>(&u);
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            if (GEGLU == 3) h[e] = *reinterpret_cast<const __half2*>(&vh[c4 * 4 + e]);
-                            else h[e] = __floats2half2_rn(v[c4 * 8 + 2 * e], v[c4 * 8 + 2 * e + 1]);
-                        }
+                        for (int e = 0; e < 4; ++e) h[e] = __floats2half2_rn(v[c4 * 8 + 2 * e], v[c4 * 8 + 2 * e + 1]);
                         *reinterpret_cast<uint4*>(p + ((uint32_t(c4) ^ sw) << 4)) = u;
                     }
                 }
@@ -475,7 +452,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 }
                 if (++ob == nob) ob = 0;
             }
-            if (++as == acc_stages) { as = 0; aph ^= 1; }
+            if (++as == 2) { as = 0; aph ^= 1; }
         }
         if (store_warp || g.warp_store) { if (elect_one()) tma_store_wait_all<0>(); __syncwarp(); }
         if (eprof && lane == 0) { g_gemm_prof[7] = clock64() - e_t0; g_gemm_prof[6] = e_wait; }
@@ -531,7 +508,7 @@ static int launch_conv_gemm(const wiw_gemm_desc* d, cudaStream_t stream) {
     g.total_tiles = (int)(((m_tiles + cg - 1) / cg) * g.n_tiles);
     static const int dbg = getenv("WIW_GEMM_DBG") ? atoi(getenv("WIW_GEMM_DBG")) : 0;
     g.dbg = dbg;
-    static const int gelu_mode = getenv("WIW_GELU") ? atoi(getenv("WIW_GELU")) : 2;         // 1 = A&S erf (2 MUFU), 2 = tanh-fit erf (1 MUFU), 3 = tanh-fit on packed halves (experimental)
+    static const int gelu_mode = getenv("WIW_GELU") ? atoi(getenv("WIW_GELU")) : 2;         // 1 = A&S erf (2 MUFU), 2 = tanh-fit erf (1 MUFU)
     static const int epi = getenv("WIW_GEMM_EPI") ? atoi(getenv("WIW_GEMM_EPI")) : 1;       // development aid for A/B runs
     g.warp_store = epi ? 1 : 0;
     // one warp's 32 rows as a (pixel, row, image) box
@@ -551,16 +528,8 @@ static int launch_conv_gemm(const wiw_gemm_desc* d, cudaStream_t stream) {
     for (int i = 0; i < d->num_taps; ++i) {
         g.tap_cbase[i] = d->tap_cbase[i]; g.tap_ox[i] = d->tap_ox[i]; g.tap_p[i] = d->tap_p[i]; g.tap_oy[i] = d->tap_oy[i];
     }
-    g.acc_stride = (g.bn <= 32) ? 32 : (g.bn <= 64 ? 64 : (g.bn <= 128 ? 128 : 256));
-    g.acc_stages = 2;
-    // experimental (not yet measured): a third accumulator stage when 3 N-tiles fit the 512 TMEM columns (bn <= 160: the N = 320
-    // layers), so the MMA warp can run a full tile further ahead of the epilogue
-    static const int acc3 = getenv("WIW_GEMM_ACC3") ? atoi(getenv("WIW_GEMM_ACC3")) : 0;
-    if (acc3 && g.bn > 128 && 3 * ((g.bn + 31) / 32 * 32) <= 512) { g.acc_stages = 3; g.acc_stride = (g.bn + 31) / 32 * 32; }
-    int cols = g.acc_stages * g.acc_stride;
-    int pow2 = 32;
-    while (pow2 < cols) pow2 *= 2;
-    g.tmem_cols = pow2;       // power of two in [64, 512]
+    int cols = 2 * ((g.bn <= 32) ? 32 : (g.bn <= 64 ? 64 : (g.bn <= 128 ? 128 : 256)));
+    g.tmem_cols = cols;       // power of two in [64, 512]
     if (cg == 2) g.tmem_cols = 512;   // pair allocations always take the whole TMEM (as CUTLASS does): both CTAs must see the same base
 
     const int stage_bytes = kBlockM * kBlockK * 2 + (g.bn / cg) * kBlockK * 2;
@@ -568,8 +537,6 @@ static int launch_conv_gemm(const wiw_gemm_desc* d, cudaStream_t stream) {
     g.out_bufs = (!g.has_res && !g.has_aux && obufs_env == 4) ? 4 : 2;
     // 8 residual slots (a whole tile's residual in flight) were tried and measured 5-17 % slower than 4: the shared memory is
     // worth more as A/B pipeline stages (profiles/r01_perf_gemm_v9_res_slots.txt).
-    static const int l2pf = getenv("WIW_GEMM_L2PF") ? atoi(getenv("WIW_GEMM_L2PF")) : 0;     // experimental (not yet measured): 0 = off
-    g.l2_prefetch = (l2pf > 0 && d->num_taps == 1 && d->k_total <= 1280) ? l2pf : 0;
     static const int rslots_env = getenv("WIW_GEMM_RSLOTS") ? atoi(getenv("WIW_GEMM_RSLOTS")) : 4;   // A/B on B200: 8 slots = 5-17 % SLOWER (they cost pipeline stages)
     g.res_slots = 4;
     {
@@ -619,14 +586,11 @@ static int launch_conv_gemm(const wiw_gemm_desc* d, cudaStream_t stream) {
         WIW_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
         WIW_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
         WIW_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
-        WIW_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
-        WIW_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
     }
     if (cg == 1) {
         int grid = num_sms();
         if (grid > g.total_tiles) grid = g.total_tiles;
-        if (g.geglu && gelu_mode == 3) conv_gemm_kernel<1, 3><<<grid, kThreads, smem_bytes, stream>>>(tm_a, tm_b, tm_out, tm_res, tm_aux, g);
-        else if (g.geglu && gelu_mode == 2) conv_gemm_kernel<1, 2><<<grid, kThreads, smem_bytes, stream>>>(tm_a, tm_b, tm_out, tm_res, tm_aux, g);
+        if (g.geglu && gelu_mode == 2) conv_gemm_kernel<1, 2><<<grid, kThreads, smem_bytes, stream>>>(tm_a, tm_b, tm_out, tm_res, tm_aux, g);
         else if (g.geglu) conv_gemm_kernel<1, 1><<<grid, kThreads, smem_bytes, stream>>>(tm_a, tm_b, tm_out, tm_res, tm_aux, g);
         else conv_gemm_kernel<1, 0><<<grid, kThreads, smem_bytes, stream>>>(tm_a, tm_b, tm_out, tm_res, tm_aux, g);
     } else {
@@ -643,8 +607,7 @@ static int launch_conv_gemm(const wiw_gemm_desc* d, cudaStream_t stream) {
         attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        if (g.geglu && gelu_mode == 3) WIW_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<2, 3>, tm_a, tm_b, tm_out, tm_res, tm_aux, g));
-        else if (g.geglu && gelu_mode == 2) WIW_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<2, 2>, tm_a, tm_b, tm_out, tm_res, tm_aux, g));
+        if (g.geglu && gelu_mode == 2) WIW_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<2, 2>, tm_a, tm_b, tm_out, tm_res, tm_aux, g));
         else if (g.geglu) WIW_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<2, 1>, tm_a, tm_b, tm_out, tm_res, tm_aux, g));
         else WIW_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<2, 0>, tm_a, tm_b, tm_out, tm_res, tm_aux, g));
     }

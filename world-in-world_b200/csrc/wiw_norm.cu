@@ -118,12 +118,7 @@ __device__ __forceinline__ uint4 gn_apply8(const uint4& u, const float* sc, cons
         const float2 f = __half22float2(h[e]);
         float a = fmaf(f.x, sc[2 * e], sh[2 * e]);
         float b = fmaf(f.y, sc[2 * e + 1], sh[2 * e + 1]);
-        if (silu == 2) {            // EXPERIMENTAL (unmeasured): x * sigmoid(x) = h + h * tanh(h), h = x / 2 -- one MUFU op instead of two
-            float ta, tb;
-            asm("tanh.approx.f32 %0, %1;" : "=f"(ta) : "f"(0.5f * a));
-            asm("tanh.approx.f32 %0, %1;" : "=f"(tb) : "f"(0.5f * b));
-            a = fmaf(0.5f * a, ta, 0.5f * a); b = fmaf(0.5f * b, tb, 0.5f * b);
-        } else if (silu) { a = silu_f(a); b = silu_f(b); }
+        if (silu) { a = silu_f(a); b = silu_f(b); }
         oh[e] = __floats2half2_rn(a, b);
     }
     return o;
@@ -386,7 +381,6 @@ extern "C" int wiw_groupnorm(const void* x, void* y, int samples, long long rows
     // Whole waves of resident CTAs: 43 chunks x 28 frames = 1204 CTAs on 592 resident slots is 2.03 waves -- the 0.03 costs a
     // full CTA time.  Round the chunk count DOWN so samples * chunks <= waves * occupancy * SMs.
     static const int wavefit = getenv("WIW_WAVEFIT") ? atoi(getenv("WIW_WAVEFIT")) : 1;       // development aid for A/B runs
-    static const int silu_mode = getenv("WIW_SILU") ? atoi(getenv("WIW_SILU")) : 1;           // 2 = tanh form (experimental, unmeasured)
     int occ_s = 4, occ_a = 4;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s, gn_stats_kernel, threads, (size_t)(2 * RL + 2) * C * sizeof(float));
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_a, gn_apply_kernel, threads, 0);
@@ -413,7 +407,7 @@ extern "C" int wiw_groupnorm(const void* x, void* y, int samples, long long rows
     const int achunks = (int)((rows_per_sample + arpc - 1) / arpc);
     gn_apply_kernel<<<dim3(achunks, samples), threads, 0, stream>>>(
         static_cast<const __half*>(x), static_cast<__half*>(y), stats, gamma, beta, rows_per_sample, C, G, (int)arpc, vpr, RL,
-        (silu && silu_mode == 2) ? 2 : silu);
+        silu);
     WIW_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
