@@ -285,23 +285,6 @@ __device__ __forceinline__ float silu_f(float x) {
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));          // e = +inf (x << 0) -> r = 0 -> silu = -0
     return x * r;
 }
-__device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
-// Exact-erf GELU (activations.py:107-123, F.gelu default) with erf from Abramowitz-Stegun 7.1.26
-// (|erf error| <= 1.5e-7, far below the fp16 output ulp): ~14 instructions instead of erff's ~40.
-//   gelu(x) = x * Phi(x),  Phi(x) = 1 - q (x >= 0) | q (x < 0),  q = 0.5 * poly(t) * exp(-z^2), z = |x|/sqrt(2), t = 1/(1 + p z)
-__device__ __forceinline__ float gelu_fast_f(float x) {
-    const float z = fabsf(x) * 0.70710678118654752440f;
-    float t;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
-    float poly = fmaf(t, 1.061405429f, -1.453152027f);
-    poly = fmaf(poly, t, 1.421413741f);
-    poly = fmaf(poly, t, -0.284496736f);
-    poly = fmaf(poly, t, 0.254829592f);
-    float e;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z * z * -1.4426950408889634f));
-    const float qh = 0.5f * poly * t * e;
-    return x >= 0.f ? fmaf(-x, qh, x) : x * qh;
-}
 // v * gelu(x) with the exact-erf GELU evaluated through ONE MUFU op:
 //   Phi(x) = 0.5 (1 + tanh(x (c0 + c1 x^2 + c2 x^4))),  odd polynomial fitted to atanh(erf(x / sqrt 2)) on |x| <= 6
 // Formula error |Phi - Phi_exact| <= 5.8e-5, |gelu - gelu_exact| <= 3.0e-5 (16x closer to erf-GELU than the classic

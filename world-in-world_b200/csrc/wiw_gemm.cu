@@ -38,7 +38,8 @@ struct GemmArgs {
     int out_cols_per_tile, geglu, has_res, has_aux;
     int tab_div, tab_mod, n_total, tmem_cols;
     int tab_stride, act, out_total;
-    int dbg;                                      // development aid: bit 0 = skip TMA loads, bit 1 = skip MMA issue (timing only)
+    int dbg;                                      // development aid (timing only, results garbage): bit 0 = skip TMA loads, bit 1 = skip MMA issue,
+                                                  // bit 3 = GEGLU epilogue multiplies value * gate without the GELU, bit 4 = skip staging + TMA stores
     int res_slots;                                // residual (aux) chunks in flight: 8 lets a whole tile's residual prefetch behind the MMAs
     int out_bufs;                                 // staging buffers per epilogue group: 4 when no residual / aux slots compete for smem, else 2
     int warp_store;                               // 1: every epilogue warp stores its own 32-row slab (no CTA barriers); 0: one store per 128-row chunk
@@ -72,7 +73,7 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmArgs& g, int tile, in
     return t;
 }
 
-template <int CG, int GEGLU>      // GEGLU: 0 = plain epilogue, 1 = GEGLU with the A&S erf (gelu_fast_f), 2 = GEGLU with the tanh-fit erf
+template <int CG, int GEGLU>      // GEGLU: 0 = plain epilogue, 2 = GEGLU epilogue (exact-erf GELU through the one-MUFU tanh fit, mul_gelu_tanhfit_f)
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                  const __grid_constant__ CUtensorMap tm_out /* box = one warp's 32 rows x 32 channels */,
@@ -349,19 +350,16 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                     for (int c = 0; c < kEpiCols / 4; ++c)
                         b4[c] = (g.bias != nullptr) ? __ldg(reinterpret_cast<const float4*>(g.bias + nb) + c) : make_float4(0, 0, 0, 0);
                     tmem_ld_wait();
+                    if (g.dbg & 8) {
+#pragma unroll
+                        for (int c = 0; c < kEpiCols; ++c) v[c] *= __uint_as_float(rg[c]);
+                    } else
 #pragma unroll
                     for (int c = 0; c < kEpiCols; c += 4) {
-                        if (GEGLU == 2) {
-                            v[c] = mul_gelu_tanhfit_f(v[c], __uint_as_float(rg[c]) + b4[c / 4].x);
-                            v[c + 1] = mul_gelu_tanhfit_f(v[c + 1], __uint_as_float(rg[c + 1]) + b4[c / 4].y);
-                            v[c + 2] = mul_gelu_tanhfit_f(v[c + 2], __uint_as_float(rg[c + 2]) + b4[c / 4].z);
-                            v[c + 3] = mul_gelu_tanhfit_f(v[c + 3], __uint_as_float(rg[c + 3]) + b4[c / 4].w);
-                        } else {
-                            v[c] *= gelu_fast_f(__uint_as_float(rg[c]) + b4[c / 4].x);
-                            v[c + 1] *= gelu_fast_f(__uint_as_float(rg[c + 1]) + b4[c / 4].y);
-                            v[c + 2] *= gelu_fast_f(__uint_as_float(rg[c + 2]) + b4[c / 4].z);
-                            v[c + 3] *= gelu_fast_f(__uint_as_float(rg[c + 3]) + b4[c / 4].w);
-                        }
+                        v[c] = mul_gelu_tanhfit_f(v[c], __uint_as_float(rg[c]) + b4[c / 4].x);
+                        v[c + 1] = mul_gelu_tanhfit_f(v[c + 1], __uint_as_float(rg[c + 1]) + b4[c / 4].y);
+                        v[c + 2] = mul_gelu_tanhfit_f(v[c + 2], __uint_as_float(rg[c + 2]) + b4[c / 4].z);
+                        v[c + 3] = mul_gelu_tanhfit_f(v[c + 3], __uint_as_float(rg[c + 3]) + b4[c / 4].w);
                     }
                 }
                 if (j == last_j) {
@@ -410,6 +408,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                     }
                     mbar_arrive(bar_rempty + 8 * rs);
                 }
+                if (g.dbg & 16) { if (++ob == nob) ob = 0; continue; }
                 // The store issued two chunks ago by this group read the buffer we are about to overwrite:
                 // the leader waits until at most one of its bulk groups is still reading, then releases the group.
                 // the store issued `nob` chunks ago read the buffer about to be overwritten
@@ -508,7 +507,6 @@ static int launch_conv_gemm(const wiw_gemm_desc* d, cudaStream_t stream) {
     g.total_tiles = (int)(((m_tiles + cg - 1) / cg) * g.n_tiles);
     static const int dbg = getenv("WIW_GEMM_DBG") ? atoi(getenv("WIW_GEMM_DBG")) : 0;
     g.dbg = dbg;
-    static const int gelu_mode = getenv("WIW_GELU") ? atoi(getenv("WIW_GELU")) : 2;         // 1 = A&S erf (2 MUFU), 2 = tanh-fit erf (1 MUFU)
     static const int epi = getenv("WIW_GEMM_EPI") ? atoi(getenv("WIW_GEMM_EPI")) : 1;       // development aid for A/B runs
     g.warp_store = epi ? 1 : 0;
     // one warp's 32 rows as a (pixel, row, image) box
@@ -582,16 +580,13 @@ static int launch_conv_gemm(const wiw_gemm_desc* d, cudaStream_t stream) {
     if (first_call_on_device(&attr_set)) {
         WIW_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
         WIW_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
-        WIW_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
-        WIW_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
         WIW_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
         WIW_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
     }
     if (cg == 1) {
         int grid = num_sms();
         if (grid > g.total_tiles) grid = g.total_tiles;
-        if (g.geglu && gelu_mode == 2) conv_gemm_kernel<1, 2><<<grid, kThreads, smem_bytes, stream>>>(tm_a, tm_b, tm_out, tm_res, tm_aux, g);
-        else if (g.geglu) conv_gemm_kernel<1, 1><<<grid, kThreads, smem_bytes, stream>>>(tm_a, tm_b, tm_out, tm_res, tm_aux, g);
+        if (g.geglu) conv_gemm_kernel<1, 2><<<grid, kThreads, smem_bytes, stream>>>(tm_a, tm_b, tm_out, tm_res, tm_aux, g);
         else conv_gemm_kernel<1, 0><<<grid, kThreads, smem_bytes, stream>>>(tm_a, tm_b, tm_out, tm_res, tm_aux, g);
     } else {
         int pairs = num_sms() / 2;
@@ -607,8 +602,7 @@ static int launch_conv_gemm(const wiw_gemm_desc* d, cudaStream_t stream) {
         attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        if (g.geglu && gelu_mode == 2) WIW_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<2, 2>, tm_a, tm_b, tm_out, tm_res, tm_aux, g));
-        else if (g.geglu) WIW_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<2, 1>, tm_a, tm_b, tm_out, tm_res, tm_aux, g));
+        if (g.geglu) WIW_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<2, 2>, tm_a, tm_b, tm_out, tm_res, tm_aux, g));
         else WIW_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<2, 0>, tm_a, tm_b, tm_out, tm_res, tm_aux, g));
     }
     WIW_CHECK_CUDA(cudaGetLastError());
