@@ -81,7 +81,7 @@ typedef struct {
     int32_t tap_p[9];
     int32_t tap_oy[9];
     int32_t tab_stride;     /* row stride of tab in elements (0 = n_total) */
-    int32_t act;            /* 0 none, 1 SiLU applied to (acc + bias + tab) */
+    int32_t act;            /* applied to (acc + bias + tab): 0 none, 1 SiLU, 2 GELU (erf), 3 quick GELU x*sigmoid(1.702x) */
     int32_t bz;             /* images per M-tile (0 or 1 = one image): lets 9-row / 18-row feature maps fill their tiles */
 } wiw_gemm_desc;
 
@@ -142,6 +142,25 @@ int wiw_frames_to_u8(const void* x, void* out, long long F, long long HW, int cs
  * x fp16 [F][HW][cs]; w fp32 [3][3][3] (co,ci,kt); out_u8 [F][3][HW] and/or out_f32 [F][3][HW] (pre-quantisation). */
 int wiw_vae_finish(const void* x, const float* w, const float* bias, void* out_u8, float* out_f32, int F,
                    long long HW, int cs, wiw_stream_t stream);
+/* ------------------------------------------------------------------------------------------
+ * Conditioning front-end (once per request): CLIP ViT image encoder of StableVideoDiffusionPipeline._encode_image
+ * (DP/pipelines/stable_video_diffusion/pipeline_stable_video_diffusion.py:183-229; the encoder itself is
+ * transformers.CLIPVisionModelWithProjection).  The Linear / LayerNorm layers go through wiw_conv_gemm / wiw_layernorm.
+ */
+/* _resize_with_antialiasing (pipeline :643-747: Gaussian blur, then bicubic with align_corners=True) as one separable linear
+ * operator per axis + the CLIP normalisation (x - mean[c]) / std[c]: uint8 planes [planes][H][W] (read as value / 255) ->
+ * fp16 [planes][oh][ow].  bounds_* int32 [out][2] = (first source index, taps), w_* fp32 [out][ksize_*] (host-built,
+ * wiw_b200/clip.py); tmp fp32 [planes][H][ow]; channel of plane p = p % channels. */
+int wiw_resize_separable_f32(const void* src, void* tmp, void* dst, long long planes, int channels, int H, int W, int oh, int ow,
+                             const int* bounds_h, const float* w_h, int ksize_h, const int* bounds_v, const float* w_v, int ksize_v,
+                             const float* mean, const float* inv_std, wiw_stream_t stream);
+/* im2col rows of a stride == kernel patch convolution (CLIPVisionEmbeddings.patch_embedding): x fp16 [B][C][G*ps][G*ps] ->
+ * fp16 [B*G*G][kpad], column (c*ps + ky)*ps + kx, zero padded to kpad (multiple of 64). */
+int wiw_patchify(const void* x, void* out, int B, int C, int G, int ps, int kpad, wiw_stream_t stream);
+/* Multi-head self-attention for short sequences, any even head_dim <= 128 (CLIPAttention: 257 tokens, 16 heads of 80):
+ * qkv fp16 [batch*S][3*heads*d] (q | k | v, head-major) -> out fp16 [batch*S][heads*d]; softmax(q k^T * scale) v in fp32. */
+int wiw_attention_small(const void* qkv, void* out, int batch, int S, int heads, int d, float scale, wiw_stream_t stream);
+
 /* Pillow-exact BICUBIC resize of uint8 planes [planes][H][W] -> [planes][oh][ow] (22-bit fixed-point two-pass resampler,
  * 8-bit intermediate in `tmp` [planes][H][ow]) followed by a 256-entry requantisation LUT: replaces the CPU
  * `img.resize(save_size, Image.BICUBIC)` + to_tensor + (clip*255).astype(uint8) of downstream/api_models/__init__.py:159-166,229.

@@ -59,6 +59,10 @@ class FakeLib:
             acc += tab[rows[..., None] * stride + np.arange(d.n_total)]
         if d.act == 1:
             acc = acc / (1.0 + np.exp(-acc))
+        elif d.act == 2:
+            acc = F.gelu(torch.from_numpy(acc)).numpy()
+        elif d.act == 3:
+            acc = acc / (1.0 + np.exp(-1.702 * acc))
         if d.geglu:
             bn, hb = d.bn, d.bn // 2
             v = acc.reshape(N, Y, X, d.n_total // bn, bn)
@@ -204,6 +208,42 @@ class FakeLib:
             y0, n = int(bv[yy, 0]), int(bv[yy, 1])
             o[:, yy, :] = np.clip(((t[:, y0:y0 + n, :] * kv[yy, :n, None]).sum(1) + (1 << 21)) >> 22, 0, 255)
         self._t(dst, (planes, oh, ow), np.uint8)[...] = self._t(lut, (256,), np.uint8)[o]
+        return 0
+
+
+    def wiw_resize_separable_f32(self, src, tmp, dst, planes, channels, H, W, oh, ow, bounds_h, w_h, ksize_h, bounds_v, w_v, ksize_v,
+                                 mean, inv_std, stream):
+        """Banded separable resampler of uint8 planes (value / 255) + (x - mean[c]) * inv_std[c], fp16 out."""
+        x = self._t(src, (planes, H, W), np.uint8).astype(np.float64) / 255.0
+        bh, kh = self._t(bounds_h, (ow, 2), np.int32), self._t(w_h, (ow, ksize_h), np.float32).astype(np.float64)
+        bv, kv = self._t(bounds_v, (oh, 2), np.int32), self._t(w_v, (oh, ksize_v), np.float32).astype(np.float64)
+        t = np.zeros((planes, H, ow))
+        for xx in range(ow):
+            x0, n = int(bh[xx, 0]), int(bh[xx, 1])
+            t[:, :, xx] = (x[:, :, x0:x0 + n] * kh[xx, :n]).sum(-1)
+        o = np.zeros((planes, oh, ow))
+        for yy in range(oh):
+            y0, n = int(bv[yy, 0]), int(bv[yy, 1])
+            o[:, yy, :] = (t[:, y0:y0 + n, :] * kv[yy, :n, None]).sum(1)
+        m, s = self._t(mean, (channels,), np.float32), self._t(inv_std, (channels,), np.float32)
+        c = np.arange(planes) % channels
+        self._t(dst, (planes, oh, ow), np.float16)[...] = ((o - m[c][:, None, None]) * s[c][:, None, None]).astype(np.float16)
+        return 0
+
+    def wiw_patchify(self, x, out, B, C, G, ps, kpad, stream):
+        img = torch.from_numpy(self._t(x, (B, C, G * ps, G * ps), np.float16).astype(np.float32))
+        cols = F.unfold(img, kernel_size=ps, stride=ps).transpose(1, 2).reshape(B * G * G, C * ps * ps)      # (c, ky, kx)-major columns
+        o = self._t(out, (B * G * G, kpad), np.float16)
+        o[...] = 0
+        o[:, : C * ps * ps] = cols.numpy().astype(np.float16)
+        return 0
+
+    def wiw_attention_small(self, qkv, out, batch, S, heads, d, scale, stream):
+        C = heads * d
+        t = torch.from_numpy(self._t(qkv, (batch, S, 3, heads, d), np.float16).astype(np.float32))
+        q, k, v = (t[:, :, i].permute(0, 2, 1, 3) for i in range(3))
+        o = torch.softmax(q @ k.transpose(-1, -2) * scale, dim=-1) @ v
+        self._t(out, (batch, S, C), np.float16)[...] = o.permute(0, 2, 1, 3).reshape(batch, S, C).numpy().astype(np.float16)
         return 0
 
 

@@ -8,7 +8,8 @@ import torch
 import wiw_b200  # noqa: F401
 from wiw_b200 import weights as W
 from wiw_b200.config import TINY_VAE
-from wiw_b200.frontend import resize_with_antialiasing, vae_encode_mode, vae_encoder_param_spec
+from wiw_b200.frontend import vae_encode_mode, vae_encoder_param_spec
+from oracle.frontend_oracle import resize_with_antialiasing
 
 
 def test_vae_encode_mode_matches_reference(golden_dir):
@@ -41,7 +42,7 @@ def test_observation_front_end_matches_reference_pipeline(golden_dir):
     (pipeline :192-200), the VAE branch a PIL-LANCZOS uint8 resize (video_processor.preprocess).  Golden = the reference
     pipeline's own _encode_image / preprocess / _encode_vae_image (oracle/make_golden_frontend_resize.py)."""
     from wiw_b200 import resize as R
-    from wiw_b200.frontend import encode_image_clip
+    from oracle.frontend_oracle import encode_image_clip
     g = np.load(os.path.join(golden_dir, "frontend_resize.npz"))
     H, Wd = int(g["height"]), int(g["width"])
     c = TINY_VAE

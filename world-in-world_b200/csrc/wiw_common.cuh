@@ -285,6 +285,13 @@ __device__ __forceinline__ float silu_f(float x) {
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));          // e = +inf (x << 0) -> r = 0 -> silu = -0
     return x * r;
 }
+// x * sigmoid(1.702 x): the "quick GELU" of OpenAI CLIP (transformers activations.QuickGELUActivation)
+__device__ __forceinline__ float quick_gelu_f(float x) {
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * (-1.702f * 1.4426950408889634f)));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+    return x * r;
+}
 // v * gelu(x) with the exact-erf GELU evaluated through ONE MUFU op:
 //   Phi(x) = 0.5 (1 + tanh(x (c0 + c1 x^2 + c2 x^4))),  odd polynomial fitted to atanh(erf(x / sqrt 2)) on |x| <= 6
 // Formula error |Phi - Phi_exact| <= 5.8e-5, |gelu - gelu_exact| <= 3.0e-5 (16x closer to erf-GELU than the classic

@@ -341,6 +341,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                     if (!GEGLU && g.act == 1) {
 #pragma unroll
                         for (int c = 0; c < kEpiCols; ++c) v[c] = silu_f(v[c]);
+                    } else if (!GEGLU && g.act == 2) {           // exact-erf GELU (CLIP ViT-H MLP, transformers ACT2FN["gelu"])
+#pragma unroll
+                        for (int c = 0; c < kEpiCols; ++c) v[c] = mul_gelu_tanhfit_f(1.0f, v[c]);
+                    } else if (!GEGLU && g.act == 3) {           // quick GELU x * sigmoid(1.702 x) (CLIPVisionConfig default)
+#pragma unroll
+                        for (int c = 0; c < kEpiCols; ++c) v[c] = quick_gelu_f(v[c]);
                     }
                 }
                 if (GEGLU) {
@@ -483,7 +489,7 @@ static int launch_conv_gemm(const wiw_gemm_desc* d, cudaStream_t stream) {
     WIW_REQUIRE(!d->tab || (d->tab_div > 0 && d->tab_mod > 0), "tab needs tab_div, tab_mod > 0");
     WIW_REQUIRE(!d->tab || !d->geglu, "tab with geglu is not supported");
     WIW_REQUIRE(!d->tab || (d->tab_stride % 8 == 0), "tab_stride must be a multiple of 8");
-    WIW_REQUIRE(d->act == 0 || d->act == 1, "act must be 0 (none) or 1 (SiLU)");
+    WIW_REQUIRE(d->act >= 0 && d->act <= 3, "act must be 0 (none), 1 (SiLU), 2 (GELU) or 3 (quick GELU)");
     WIW_REQUIRE(!(d->act && d->geglu), "act with geglu is not supported");
 
     GemmArgs g;

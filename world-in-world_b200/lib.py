@@ -64,6 +64,9 @@ SYMBOLS = {
     "wiw_frames_to_u8": (_I, [_VP, _VP, _LL, _LL, _I, _VP]),
     "wiw_vae_finish": (_I, [_VP, _VP, _VP, _VP, _VP, _I, _LL, _I, _VP]),
     "wiw_resize_bicubic_u8": (_I, [_VP, _VP, _VP, _LL, _I, _I, _I, _I, _VP, _VP, _I, _VP, _VP, _I, _VP, _VP]),
+    "wiw_resize_separable_f32": (_I, [_VP, _VP, _VP, _LL, _I, _I, _I, _I, _I, _VP, _VP, _I, _VP, _VP, _I, _VP, _VP, _VP]),
+    "wiw_patchify": (_I, [_VP, _VP, _I, _I, _I, _I, _I, _VP]),
+    "wiw_attention_small": (_I, [_VP, _VP, _I, _I, _I, _I, _F, _VP]),
     "wiw_nchw_to_nhwc": (_I, [_VP, _VP, _LL, _I, _LL, _I, _VP]),
     "wiw_nhwc_to_nchw": (_I, [_VP, _VP, _LL, _I, _LL, _I, _VP]),
 }
@@ -71,7 +74,7 @@ SYMBOLS = {
 
 # launch accounting for bench.py's `gpu_launches` (kernels launched by each C-ABI call)
 COUNTERS = {"gpu_launches": 0}
-KERNELS_PER_CALL = {"wiw_groupnorm": 3, "wiw_resize_bicubic_u8": 2}
+KERNELS_PER_CALL = {"wiw_groupnorm": 3, "wiw_resize_bicubic_u8": 2, "wiw_resize_separable_f32": 2}
 _NO_LAUNCH = {"wiw_last_error", "wiw_abi_version", "wiw_device_ok", "wiw_groupnorm_workspace_floats"}
 
 

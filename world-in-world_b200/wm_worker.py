@@ -204,7 +204,10 @@ class Navigator:
         self.image_width, self.image_height = args.width, args.height
         self.num_frames = args.num_frames
         self.rollout = rollout
-        self.image_encoder = image_encoder
+        # CLIP ViT image encoder on the sm_100a kernels (wiw_b200/clip.py); `image_encoder` is either a ready ClipVisionEngine or
+        # the transformers module holding the checkpoint (its state dict is re-laid-out once, the module itself is not called)
+        from .clip import ClipVisionEngine
+        self.image_encoder = image_encoder if isinstance(image_encoder, ClipVisionEngine) else ClipVisionEngine.from_module(image_encoder, device)
         self.vae_encoder_sd = vae_encoder_sd
         self.device = torch.device(device)
         self.generator = torch.Generator(device=self.device).manual_seed(1)        # eval_inference.py:97
@@ -224,7 +227,7 @@ class Navigator:
         dev = self.device
         H, W = self.image_height, self.image_width
         obs = torch.from_numpy(np.ascontiguousarray(images_u8[:, :3])).to(dev)               # uint8 [b, 3, Hin, Win]
-        emb = frontend.encode_image_clip(obs.float() / 255.0, self.image_encoder)             # pil_to_numpy/numpy_to_pt: [0,1]; [b, 1, D]
+        emb = self.image_encoder(obs)                                                         # [b, 1, D]: resize -> normalise -> ViT, wiw_b200/clip.py
         if tuple(obs.shape[-2:]) != (H, W):
             key = (int(obs.shape[-2]), int(obs.shape[-1]), H, W)
             if getattr(self, "_obs_resizer_key", None) != key:
