@@ -394,8 +394,9 @@ def main():
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         e2e = {"value": n_req * F * reps / float(dt.item()), "unit": "frames/s", "h2d_bytes_per_step": int(b_image.nbytes + b_action.nbytes),
                "d2h_bytes_per_step": int(n_req * F * 3 * 480 * 480), "api": api,
-               "includes": "H2D of the uint8 observation(s), CLIP ViT-H + fp32 VAE encode (PyTorch), 25-step rollout, decode, "
-                           "Pillow-exact bicubic 480x480 + requantisation on the GPU, D2H of the uint8 frames"}
+               "includes": "H2D of the uint8 observation(s), CLIP ViT-H/14 on this library's kernels (antialiased resize + 32 layers), fp32 VAE "
+                           "encode (PyTorch library kernels, as the reference's force_upcast), 25-step rollout, decode, Pillow-exact "
+                           "bicubic 480x480 + requantisation on the GPU, D2H of the uint8 frames"}
 
     # ---- latency mode for fewer branches than GPUs: ONE branch on the pair (rank 0, rank 1), one CFG row each
     cfg_split_ms = None
