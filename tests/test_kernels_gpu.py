@@ -84,7 +84,7 @@ def test_attention_spatial_peaky_rows():
     close(y, ref, "attn peaky", rel=6e-3, abs_scale=4e-3)
 
 
-@pytest.mark.parametrize("b,f,s,c", [(2, 8, 128, 64), (2, 14, 144, 128), (1, 14, 50, 320), (2, 8, 2, 128)])
+@pytest.mark.parametrize("b,f,s,c", [(2, 8, 128, 64), (2, 14, 144, 128), (1, 14, 50, 320), (2, 8, 2, 128), (1, 25, 40, 64)])
 def test_attention_temporal(b, f, s, c):
     qkv = rnd(b * f * s, 3 * c, seed=1).half().to(DEV)
     y = ops.attention_temporal(qkv, b, f, s, c)

@@ -392,15 +392,9 @@ extern "C" int wiw_attention_temporal_mma(const void* qkv, void* out, int B, int
 extern "C" int wiw_attention_temporal(const void* qkv, void* out, int B, int F, int S, int C, wiw_stream_t st) {
     WIW_REQUIRE(qkv && out && C % 64 == 0, "bad args");
     if (F <= 16) return wiw_attention_temporal_mma(qkv, out, B, F, S, C, st);     // warp-level tensor-core kernel
-    switch (F) {
-        case 2: return launch_tattn<2>(qkv, out, B, S, C, STREAM(st));
-        case 4: return launch_tattn<4>(qkv, out, B, S, C, STREAM(st));
-        case 8: return launch_tattn<8>(qkv, out, B, S, C, STREAM(st));
-        case 14: return launch_tattn<14>(qkv, out, B, S, C, STREAM(st));
-        case 16: return launch_tattn<16>(qkv, out, B, S, C, STREAM(st));
-        case 25: return launch_tattn<25>(qkv, out, B, S, C, STREAM(st));
-        default: wiw::set_last_error("temporal attention is built for F in {2,4,8,14,16,25}"); return 2;
-    }
+    if (F == 25) return launch_tattn<25>(qkv, out, B, S, C, STREAM(st));             // SVD-XT clip length: scalar kernel
+    wiw::set_last_error("temporal attention is built for F <= 16 (tensor-core kernel) and F == 25");
+    return 2;
 }
 
 extern "C" int wiw_softmax_rows(void* s, long long rows, int S, float scale, wiw_stream_t st) {
