@@ -336,6 +336,19 @@ def main():
             with open(os.path.join(REPO, "gpurun_out", "gemm_profile.json"), "w") as f:
                 json.dump([{"shape": k, "launches": v[0], "tflop": v[1] / 1e12, "ms": v[2], "tflops": v[1] / v[2] / 1e9}
                            for k, v in sorted(by_shape.items(), key=lambda kv: -kv[1][2])], f, indent=1)
+            # the same per-shape table for the temporal-VAE decode (its GEMM launches, live CUDA events)
+            ops.PROFILE = []
+            ro.decode(lat_nhwc)
+            torch.cuda.synchronize()
+            vprof, ops.PROFILE = ops.PROFILE, None
+            by_shape = {}
+            for p in vprof:
+                e = by_shape.setdefault(p[3], [0, 0.0, 0.0])
+                e[0] += 1; e[1] += p[0]; e[2] += p[1].elapsed_time(p[2])
+            with open(os.path.join(REPO, "gpurun_out", "gemm_profile_vae.json"), "w") as f:
+                json.dump({"decode_ms": dec_ms, "gemm_ms": sum(v[2] for v in by_shape.values()), "gemm_tflop": sum(v[1] for v in by_shape.values()) / 1e12,
+                           "shapes": [{"shape": k, "launches": v[0], "tflop": v[1] / 1e12, "ms": v[2], "tflops": v[1] / v[2] / 1e9}
+                                      for k, v in sorted(by_shape.items(), key=lambda kv: -kv[1][2])]}, f, indent=1)
         peak, hbm, how = peaks()
         ach = g_flop / (g_ms * 1e-3) / 1e12
         roof = {"bound": "tensor", "kernel": "conv_gemm_kernel (tcgen05 implicit GEMM: all Linear/Conv2d/Conv3d of the UNet)",
