@@ -9,8 +9,10 @@
 //   warp 1     tcgen05.mma issuer: S_t = Q_t K_j^T (M128 N128 K64, K-major x K-major) -> TMEM,
 //              O_t += P_t V_j (M128 N64 K128, A = P_t from smem, B = V consumed MN-major from its TMA tile)
 //   warps 2-5  softmax of tile 0, warps 6-9 softmax of tile 1 (one thread per query row):
-//              tcgen05.ld S (2 passes: max, then exp2), P -> fp16 -> swizzled smem, lazy rescale of O in TMEM
-//              when some row max of the warp grew by more than 2^8.  The row sum l is NOT accumulated by the
+//              ONE tcgen05.ld sweep: the row's 128 scores stay in registers (max, then exp2 from registers) and S_t goes back to the
+//              tensor core immediately, so QK^T of the next KV tile overlaps this tile's exponentials (+2.8 % at S = 9216, +5.6 % at
+//              S = 576 over the two-sweep version, profiles/r02_perf_attn_onepass_ab.txt); P -> fp16 -> swizzled smem, lazy rescale
+//              of O in TMEM when some row max of the warp grew by more than 2^8.  The row sum l is NOT accumulated by the
 //              softmax threads: the PV MMA runs with N = 80 where B columns 64..79 come from a tile of ones, so
 //              O[:, 64] = sum_k P[:, k] in fp32 for free.  Final O / l -> fp16 -> TMA store.
 #include "wiw_common.cuh"
@@ -207,12 +209,14 @@ attn_spatial_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
                 const int sk = ik % kRing, sv = iv % kRing;
                 if (more) mbar_wait(bar_full + 8 * sk, (uint32_t)(ik / kRing) & 1u);      // K_{j+1}
                 mbar_wait(bar_full + 8 * sv, (uint32_t)(iv / kRing) & 1u);                // V_j
-                for (int t = 0; t < 2; ++t) {
-                    if (more) {
-                        mbar_wait(bar_s_free + 8 * t, (uint32_t)j & 1u);      // softmax t finished reading S_t of tile j
+                if (more) {
+                    for (int t = 0; t < 2; ++t) {
+                        mbar_wait(bar_s_free + 8 * t, (uint32_t)j & 1u);      // the scores of tile j are in softmax t's registers
                         tc_fence_after();
                         issue_qk(t, sk);
                     }
+                }
+                for (int t = 0; t < 2; ++t) {
                     mbar_wait(bar_p_full + 8 * t, (uint32_t)j & 1u);          // P_t of tile j is in smem
                     tc_fence_after();
                     issue_pv(t, sv, j == 0);
@@ -240,32 +244,23 @@ attn_spatial_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
             const bool masked = valid < kKV;
             mbar_wait(bar_s_full + 8 * t, (uint32_t)j & 1u);
             tc_fence_after();
-            // pass 1: row max.  The TMEM load of chunk ch+1 is in flight while chunk ch is reduced.
-            float mx = -INFINITY;
-            if (!masked) {
-                uint32_t ra[32], rb[32];
-                tmem_ld_32x32b_x32(tS, ra);
-                tmem_ld_wait();
-                tmem_ld_32x32b_x32(tS + 32, rb);
-                mx = row_max_chunk(ra, mx);
-                tmem_ld_wait();
-                tmem_ld_32x32b_x32(tS + 64, ra);
-                mx = row_max_chunk(rb, mx);
-                tmem_ld_wait();
-                tmem_ld_32x32b_x32(tS + 96, rb);
-                mx = row_max_chunk(ra, mx);
-                tmem_ld_wait();
-                mx = row_max_chunk(rb, mx);
-            } else {                                             // ragged last KV tile (S % 128 != 0): simple rolled loop
-#pragma unroll 1
-                for (int ch = 0; ch < 4; ++ch) {
-                    uint32_t r[32];
-                    tmem_ld_32x32b_x32(tS + ch * 32, r);
-                    tmem_ld_wait();
-                    mask_chunk(r, ch * 32, valid);
-                    mx = row_max_chunk(r, mx);
-                }
+            // ONE sweep: the 128 scores of this row go to registers and stay there; S_t is handed back to the tensor core at once,
+            // so QK^T of the next KV tile runs under this tile's exponentials (the registers are the second score buffer)
+            uint32_t sc[128];
+            tmem_ld_32x32b_x32(tS, sc);
+            tmem_ld_32x32b_x32(tS + 32, sc + 32);
+            tmem_ld_32x32b_x32(tS + 64, sc + 64);
+            tmem_ld_32x32b_x32(tS + 96, sc + 96);
+            tmem_ld_wait();
+            tc_fence_before();
+            mbar_arrive(bar_s_free + 8 * t);
+            if (masked) {
+#pragma unroll
+                for (int ch = 0; ch < 4; ++ch) mask_chunk(sc + 32 * ch, ch * 32, valid);
             }
+            float mx = -INFINITY;
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch) mx = row_max_chunk(sc + 32 * ch, mx);
             float alpha = 1.f;
             const bool grow = (mx - m_ref) * c > kRescaleThreshold;
             const bool any_grow = __any_sync(0xffffffffu, grow) || (j == 0);
@@ -291,38 +286,12 @@ attn_spatial_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
                     tmem_st_wait();
                 }
             }
-            // pass 2: p = 2^((s - m_ref) * c) in packed fp16 -> P smem (K-major, SWIZZLE_128B, two 64-key halves)
+            // p = 2^((s - m_ref) * c) in packed fp16 -> P smem (K-major, SWIZZLE_128B, two 64-key halves)
             const float mc = m_ref * c;
-            if (!masked) {
-                uint32_t ra[32], rb[32];
-                tmem_ld_32x32b_x32(tS, ra);
-                tmem_ld_wait();
-                tmem_ld_32x32b_x32(tS + 32, rb);
-                exp_chunk<POLY>(ra, 0, c, mc, pP, sw);
-                tmem_ld_wait();
-                tmem_ld_32x32b_x32(tS + 64, ra);
-                exp_chunk<POLY>(rb, 1, c, mc, pP, sw);
-                tmem_ld_wait();
-                tmem_ld_32x32b_x32(tS + 96, rb);
-                exp_chunk<POLY>(ra, 2, c, mc, pP + kTileBytes, sw);
-                tmem_ld_wait();
-                tc_fence_before();                               // last read of S_t: release it for the next QK
-                mbar_arrive(bar_s_free + 8 * t);
-                exp_chunk<POLY>(rb, 3, c, mc, pP + kTileBytes, sw);
-            } else {
-#pragma unroll 1
-                for (int ch = 0; ch < 4; ++ch) {
-                    uint32_t r[32];
-                    tmem_ld_32x32b_x32(tS + ch * 32, r);
-                    tmem_ld_wait();
-                    if (ch == 3) {
-                        tc_fence_before();
-                        mbar_arrive(bar_s_free + 8 * t);
-                    }
-                    mask_chunk(r, ch * 32, valid);
-                    exp_chunk<POLY>(r, ch, c, mc, pP + (ch >> 1) * kTileBytes, sw);
-                }
-            }
+            exp_chunk<POLY>(sc, 0, c, mc, pP, sw);
+            exp_chunk<POLY>(sc + 32, 1, c, mc, pP, sw);
+            exp_chunk<POLY>(sc + 64, 2, c, mc, pP + kTileBytes, sw);
+            exp_chunk<POLY>(sc + 96, 3, c, mc, pP + kTileBytes, sw);
             fence_proxy_async_smem();
             tc_fence_before();
             mbar_arrive(bar_p_full + 8 * t);
