@@ -6,9 +6,10 @@
 // One CTA (one per SM) = 256 query rows (two 128-row tiles) of one (image, head); the two tiles
 // ping-pong so the tensor core works on one while the other is in softmax.  Per KV tile of 128 keys:
 //   warp 0     TMA: Q0,Q1 once, then K_j / V_j tiles ([128][64] fp16, SWIZZLE_128B) through a 4-slot ring
-//   warp 1     tcgen05.mma issuer: S_t = Q_t K_j^T (M128 N128 K64, K-major x K-major) -> TMEM,
+//   warps 1,2  tcgen05.mma issuers, ONE PER Q TILE (each tile's QK^T / PV chain waits only on its own softmax warps):
+//              S_t = Q_t K_j^T (M128 N128 K64, K-major x K-major) -> TMEM,
 //              O_t += P_t V_j (M128 N64 K128, A = P_t from smem, B = V consumed MN-major from its TMA tile)
-//   warps 2-5  softmax of tile 0, warps 6-9 softmax of tile 1 (one thread per query row):
+//   warps 3-6  softmax of tile 0, warps 7-10 softmax of tile 1 (one thread per query row):
 //              ONE tcgen05.ld sweep: the row's 128 scores stay in registers (max, then exp2 from registers) and S_t goes back to the
 //              tensor core immediately, so QK^T of the next KV tile overlaps this tile's exponentials (+2.8 % at S = 9216, +5.6 % at
 //              S = 576 over the two-sweep version, profiles/r02_perf_attn_onepass_ab.txt); P -> fp16 -> swizzled smem, lazy rescale
@@ -23,10 +24,11 @@ namespace wiw {
 constexpr int kQ = 128, kKV = 128, kD = 64;
 constexpr int kTileBytes = 128 * 64 * 2;        // 16 KB: a Q / K / V tile and each 64-key half of P
 constexpr int kRing = 4;
-constexpr int kAttnThreads = 10 * 32;
+constexpr int kAttnThreads = 11 * 32;
 constexpr int kAttnSmem = 1024 + kTileBytes * (2 + kRing + 1 + 4) + 256;   // Q0,Q1 | K/V ring | ones | P0,P1
 constexpr uint32_t kTmemCols = 512;              // S0 [0,128) S1 [128,256) O0 [256,336) O1 [384,464)
 constexpr int kOCols = 80;                       // 64 output columns + 16 copies of the row sum l (P @ ones)
+constexpr int kStaggerCycles = 1000;
 constexpr float kRescaleThreshold = 8.0f;        // log2 units (P <= 2^8 fits fp16 comfortably)
 
 __device__ __forceinline__ uint32_t cvt_f16x2(float lo, float hi) {
@@ -123,7 +125,7 @@ attn_spatial_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
         tma_prefetch_desc(&tm_qkv);
         tma_prefetch_desc(&tm_out);
         mbar_init(bar_q, 1);
-        for (int i = 0; i < kRing; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 1); }
+        for (int i = 0; i < kRing; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 2); }
         for (int t = 0; t < 2; ++t) {
             mbar_init(bar_s_full + 8 * t, 1);
             mbar_init(bar_s_free + 8 * t, 128);
@@ -164,73 +166,64 @@ attn_spatial_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
             }
             __syncwarp();
         }
-    } else if (warp == 1) {
-        // ================================ MMA issuer ================================
-        {
-            const uint32_t idesc_qk = make_idesc_f16(kKV, 0, 0);
-            const uint32_t idesc_pv = make_idesc_f16(kOCols, 0, 1);           // B (= [V | ones]) is MN-major, N = 80
-            auto issue_qk = [&](int t, int stage) {
-                const uint64_t dq = make_desc_sw128(sQ + t * kTileBytes), dk = make_desc_sw128(sRing + stage * kTileBytes);
-                if (elect_one()) {
+    } else if (warp <= 2) {
+        // ================================ MMA issuer of tile t = warp - 1 ================================
+        const int t = warp - 1;
+        const uint32_t idesc_qk = make_idesc_f16(kKV, 0, 0);
+        const uint32_t idesc_pv = make_idesc_f16(kOCols, 0, 1);
+        auto issue_qk = [&](int stage) {
+            const uint64_t dq = make_desc_sw128(sQ + t * kTileBytes), dk = make_desc_sw128(sRing + stage * kTileBytes);
+            if (elect_one()) {
 #pragma unroll
-                    for (int kk = 0; kk < kD / 16; ++kk)
-                        umma_f16_ss(tmem_base + t * 128, dq + 2 * kk, dk + 2 * kk, idesc_qk, kk > 0 ? 1u : 0u);
-                    umma_commit(bar_s_full + 8 * t);
-                }
-                __syncwarp();
-            };
-            auto issue_pv = [&](int t, int stage, bool first) {
-                // MN-major B: N-atom 0 (columns 0..63) = the V tile, N-atom 1 (columns 64..79) = the ones tile at +LBO;
-                // K groups of 8 rows at SBO = 1024 B.  O[:, 64..79] therefore accumulates the row sums of P in fp32.
-                const uint32_t v_addr = sRing + stage * kTileBytes;
-                const uint64_t dv = (uint64_t((v_addr & 0x3FFFF) >> 4)) | (uint64_t((sOnes - v_addr) >> 4) << 16) |
-                                    (uint64_t(1024 >> 4) << 32) | (uint64_t(1) << 46) | (uint64_t(2) << 61);
-                const uint64_t dp0 = make_desc_sw128(sP + t * 2 * kTileBytes);
-                if (elect_one()) {
-#pragma unroll
-                    for (int kk = 0; kk < kKV / 16; ++kk) {
-                        const uint64_t dp = dp0 + (uint64_t)((kk >> 2) * (kTileBytes >> 4) + 2 * (kk & 3));
-                        umma_f16_ss(tmem_base + 256 + t * 128, dp, dv + (uint64_t)kk * (2048 >> 4), idesc_pv, (!first || kk > 0) ? 1u : 0u);
-                    }
-                    umma_commit(bar_pv_done + 8 * t);
-                }
-                __syncwarp();
-            };
-            mbar_wait(bar_q, 0);
-            mbar_wait(bar_full + 0, 0);                                       // K_0 in ring slot 0
-            tc_fence_after();
-            issue_qk(0, 0);
-            issue_qk(1, 0);
-            if (elect_one()) umma_commit(bar_empty + 0);
-            __syncwarp();
-            for (int j = 0; j < nkv; ++j) {
-                const bool more = (j + 1 < nkv);
-                const int ik = 2 * j + 2, iv = 2 * j + 1;
-                const int sk = ik % kRing, sv = iv % kRing;
-                if (more) mbar_wait(bar_full + 8 * sk, (uint32_t)(ik / kRing) & 1u);      // K_{j+1}
-                mbar_wait(bar_full + 8 * sv, (uint32_t)(iv / kRing) & 1u);                // V_j
-                if (more) {
-                    for (int t = 0; t < 2; ++t) {
-                        mbar_wait(bar_s_free + 8 * t, (uint32_t)j & 1u);      // the scores of tile j are in softmax t's registers
-                        tc_fence_after();
-                        issue_qk(t, sk);
-                    }
-                }
-                for (int t = 0; t < 2; ++t) {
-                    mbar_wait(bar_p_full + 8 * t, (uint32_t)j & 1u);          // P_t of tile j is in smem
-                    tc_fence_after();
-                    issue_pv(t, sv, j == 0);
-                }
-                if (elect_one()) {
-                    if (more) umma_commit(bar_empty + 8 * sk);
-                    umma_commit(bar_empty + 8 * sv);
-                }
-                __syncwarp();
+                for (int kk = 0; kk < kD / 16; ++kk)
+                    umma_f16_ss(tmem_base + t * 128, dq + 2 * kk, dk + 2 * kk, idesc_qk, kk > 0 ? 1u : 0u);
+                umma_commit(bar_s_full + 8 * t);
+                umma_commit(bar_empty + 8 * stage);
             }
+            __syncwarp();
+        };
+        auto issue_pv = [&](int stage, bool first) {
+            const uint32_t v_addr = sRing + stage * kTileBytes;
+            const uint64_t dv = (uint64_t((v_addr & 0x3FFFF) >> 4)) | (uint64_t((sOnes - v_addr) >> 4) << 16) |
+                                (uint64_t(1024 >> 4) << 32) | (uint64_t(1) << 46) | (uint64_t(2) << 61);
+            const uint64_t dp0 = make_desc_sw128(sP + t * 2 * kTileBytes);
+            if (elect_one()) {
+#pragma unroll
+                for (int kk = 0; kk < kKV / 16; ++kk) {
+                    const uint64_t dp = dp0 + (uint64_t)((kk >> 2) * (kTileBytes >> 4) + 2 * (kk & 3));
+                    umma_f16_ss(tmem_base + 256 + t * 128, dp, dv + (uint64_t)kk * (2048 >> 4), idesc_pv, (!first || kk > 0) ? 1u : 0u);
+                }
+                umma_commit(bar_pv_done + 8 * t);
+                umma_commit(bar_empty + 8 * stage);
+            }
+            __syncwarp();
+        };
+        mbar_wait(bar_q, 0);
+        mbar_wait(bar_full + 0, 0);
+        // The two tiles' chains are independent; started together they run in lockstep and leave the MUFU / issue pipes idle
+        // during both tiles' load-max-wait phases.  Tile 1 starts ~a third of a KV-tile period late, which the chains then keep
+        // (same-box A/B: 820 TFLOP/s without the offset, 851 with 900-1700 cycles; profiles/r02_perf_attn_mma2_stagger_ab.txt)
+        if (t == 1) { const long long t0 = clock64(); while (clock64() - t0 < kStaggerCycles) {} }
+        tc_fence_after();
+        issue_qk(0);
+        for (int j = 0; j < nkv; ++j) {
+            const bool more = (j + 1 < nkv);
+            const int ik = 2 * j + 2, iv = 2 * j + 1;
+            const int sk = ik % kRing, sv = iv % kRing;
+            if (more) {
+                mbar_wait(bar_full + 8 * sk, (uint32_t)(ik / kRing) & 1u);
+                mbar_wait(bar_s_free + 8 * t, (uint32_t)j & 1u);
+                tc_fence_after();
+                issue_qk(sk);
+            }
+            mbar_wait(bar_full + 8 * sv, (uint32_t)(iv / kRing) & 1u);
+            mbar_wait(bar_p_full + 8 * t, (uint32_t)j & 1u);
+            tc_fence_after();
+            issue_pv(sv, j == 0);
         }
     } else {
         // ================= softmax / correction / epilogue: one thread per query row of tile t =================
-        const int t = (warp - 2) >> 2;
+        const int t = (warp - 3) >> 2;
         const int qd = warp & 3;
         const int row = qd * 32 + lane;
         const uint32_t lane_sel = (uint32_t)(qd * 32) << 16;
@@ -325,7 +318,7 @@ attn_spatial_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
         fence_proxy_async_smem();
         if (t == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
         else        asm volatile("bar.sync 2, 128;" ::: "memory");
-        if (qd == 2 && lane == 0) {                              // first warp of each softmax group (warps 2 and 6)
+        if (((warp - 3) & 3) == 0 && lane == 0) {
             asm volatile(
                 "cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
                 ::"l"(reinterpret_cast<uint64_t>(&tm_out)), "r"(sP + t * 2 * kTileBytes), "r"(head * kD), "r"(q0 + t * kQ), "r"(img) : "memory");
