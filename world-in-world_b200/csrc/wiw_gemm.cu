@@ -51,7 +51,7 @@ struct GemmArgs {
 };
 
 // development aid (WIW_GEMM_DBG bit 2): cycle counters of CTA 0's producer / MMA / first epilogue warp, read by wiw_debug_gemm_prof
-__device__ long long g_gemm_prof[8];
+__device__ long long g_gemm_prof[24];     // [8..15]: epilogue phases of CTA 0 warp 3 (see eph_* below), [16] chunks
 
 struct TileCoord {
     int x0, y0, img, n_tile;
@@ -272,6 +272,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         int chunks = 0;
         const bool eprof = (g.dbg & 4) && blockIdx.x == 0 && warp == 3;
         long long e_wait = 0;
+        long long eph[8] = {0, 0, 0, 0, 0, 0, 0, 0}, ech = 0, ets = 0;      // per-phase cycle sums: ld+bias | math | release | residual | wait_read | sts+fence | tma issue
+#define EPH(i) do { if (eprof) { const long long _n = clock64(); eph[i] += _n - ets; ets = _n; } } while (0)
         const long long e_t0 = eprof ? clock64() : 0;
         for (int tile = first_tile; tile < g.total_tiles; tile += tile_step, chunk_base += chunks) {
             const TileCoord t = decode_tile<CG>(g, tile, cta_rank);
@@ -298,6 +300,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 if (lane == 0) { if (CG == 2) mbar_arrive_cluster(bar_tempty + 8 * as, 0); else mbar_arrive(bar_tempty + 8 * as); }
             }
             for (int j = grp; j < chunks; j += 2) {
+                if (eprof) { ets = clock64(); ++ech; }
                 float v[kEpiCols];
                 uint32_t rg[kEpiCols];                              // gate half of a GEGLU tile
                 const int half_n = g.bn >> 1;
@@ -349,6 +352,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                         for (int c = 0; c < kEpiCols; ++c) v[c] = quick_gelu_f(v[c]);
                     }
                 }
+                EPH(0);
                 if (GEGLU) {
                     const int nb = acc_n0 + half_n + j * kEpiCols;
                     float4 b4[kEpiCols / 4];
@@ -368,6 +372,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                         v[c + 3] = mul_gelu_tanhfit_f(v[c + 3], __uint_as_float(rg[c + 3]) + b4[c / 4].w);
                     }
                 }
+                EPH(1);
                 if (j == last_j) {
                     // this group's TMEM reads of the accumulator stage are done: hand it back to the MMA warp
                     tc_fence_before();
@@ -378,6 +383,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 #pragma unroll
                     for (int c = 0; c < kEpiCols; ++c) v[c] *= g.s_acc;
                 }
+                EPH(2);
                 if (has_epi_loads) {
                     const long long n = chunk_base + j;                       // global chunk index of this CTA
                     const int rs = int(n % g.res_slots);
@@ -414,6 +420,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                     }
                     mbar_arrive(bar_rempty + 8 * rs);
                 }
+                EPH(3);
                 if (g.dbg & 16) { if (++ob == nob) ob = 0; continue; }
                 // The store issued two chunks ago by this group read the buffer we are about to overwrite:
                 // the leader waits until at most one of its bulk groups is still reading, then releases the group.
@@ -425,6 +432,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                     if (store_warp) { if (elect_one()) { if (nob == 4) tma_store_wait_read<3>(); else tma_store_wait_read<1>(); } __syncwarp(); }
                     asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
                 }
+                EPH(4);
                 {
                     uint8_t* p = smem_raw + (out_base - smem_u32(smem_raw)) + (grp * nob + ob) * kEpiChunkBytes + row_off;
 #pragma unroll
@@ -437,6 +445,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                     }
                 }
                 fence_proxy_async_smem();
+                EPH(5);
                 if (g.warp_store) {
                     __syncwarp();                                  // the slab is complete and visible to the async proxy
                     if (elect_one()) {
@@ -455,10 +464,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                         __syncwarp();
                     }
                 }
+                EPH(6);
                 if (++ob == nob) ob = 0;
             }
             if (++as == 2) { as = 0; aph ^= 1; }
         }
+        if (eprof && lane == 0) { for (int i = 0; i < 8; ++i) g_gemm_prof[8 + i] = eph[i]; g_gemm_prof[16] = ech; }
         if (store_warp || g.warp_store) { if (elect_one()) tma_store_wait_all<0>(); __syncwarp(); }
         if (eprof && lane == 0) { g_gemm_prof[7] = clock64() - e_t0; g_gemm_prof[6] = e_wait; }
     }
@@ -617,8 +628,8 @@ static int launch_conv_gemm(const wiw_gemm_desc* d, cudaStream_t stream) {
 
 }  // namespace wiw
 
-extern "C" int wiw_debug_gemm_prof(long long* out8) {
-    return cudaMemcpyFromSymbol(out8, wiw::g_gemm_prof, 8 * sizeof(long long)) == cudaSuccess ? 0 : 1;
+extern "C" int wiw_debug_gemm_prof(long long* out24) {
+    return cudaMemcpyFromSymbol(out24, wiw::g_gemm_prof, 24 * sizeof(long long)) == cudaSuccess ? 0 : 1;
 }
 
 extern "C" int wiw_conv_gemm(const wiw_gemm_desc* d, wiw_stream_t stream) {
