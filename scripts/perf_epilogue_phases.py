@@ -1,14 +1,14 @@
 """Cycle budget of one epilogue warp of conv_gemm_kernel (CTA 0, warp 3) per 32-column chunk, by phase (WIW_GEMM_DBG=4):
 TMEM load + bias/table | activation math | accumulator release | residual | wait for the staging buffer | STS + proxy fence | TMA issue."""
 import ctypes, os, sys
-os.environ["WIW_GEMM_DBG"] = "4"
+os.environ["WIW_GEMM_DBG"] = str(4 | int(os.environ.get("EXTRA_DBG", "0")))
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import wiw_b200  # noqa
 from wiw_b200 import lib as L, ops
 DEV = "cuda"
 lib = ctypes.CDLL(L.LIB_PATH)
-names = ["ld+bias", "math", "release", "residual", "wait_read", "sts+fence", "tma issue"]
+names = ["bias add", "math", "release(+prefetch)", "residual", "wait_read", "sts+fence", "tma issue", "tmem ld+wait"]
 
 
 def report(tag, fn, flop):
@@ -24,7 +24,7 @@ def report(tag, fn, flop):
     ch = max(v[16], 1)
     print(f"{tag}: {ms:.4f} ms {flop / ms / 1e9:.0f} TFLOP/s | MMA warp: total {v[0]} cyc, wait data {v[1]}, wait acc-empty {v[2]} | epilogue warp: total {v[7]}, "
           f"wait acc-full {v[6]}, chunks {v[16]}")
-    print("      cycles per chunk: " + ", ".join(f"{n} {v[8 + i] / ch:.0f}" for i, n in enumerate(names)) + f" | sum {sum(v[8:15]) / ch:.0f}", flush=True)
+    print("      cycles per chunk: " + ", ".join(f"{n} {v[8 + i] / ch:.0f}" for i, n in enumerate(names)) + f" | sum {sum(v[8:16]) / ch:.0f}", flush=True)
 
 
 m, c = 258048, 320

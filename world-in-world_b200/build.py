@@ -12,6 +12,14 @@ LIB = os.path.join(HERE, "libwiw_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
+# Development variants (never the product library): WIW_BUILD_VARIANT=phases adds -DWIW_GEMM_PHASES (per-phase epilogue cycle
+# counters) and writes libwiw_b200_phases.so + build_phases/; select it at run time with WIW_B200_LIB.
+VARIANT = os.environ.get("WIW_BUILD_VARIANT", "")
+VARIANT_DEFS = {"phases": ["-DWIW_GEMM_PHASES"]}
+if VARIANT:
+    FLAGS = FLAGS + VARIANT_DEFS[VARIANT]
+    LIB = os.path.join(HERE, f"libwiw_b200_{VARIANT}.so")
+BUILD_DIR = os.path.join(HERE, "build" + (f"_{VARIANT}" if VARIANT else ""))
 
 
 def sources():
@@ -30,10 +38,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB
     objs = []
-    os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+    os.makedirs(BUILD_DIR, exist_ok=True)
     procs = []
     for src in sources():
-        obj = os.path.join(HERE, "build", os.path.basename(src).replace(".cu", ".o"))
+        obj = os.path.join(BUILD_DIR, os.path.basename(src).replace(".cu", ".o"))
         objs.append(obj)
         if (not force and os.path.exists(obj) and os.path.getmtime(obj) > os.path.getmtime(src)
                 and all(os.path.getmtime(obj) > os.path.getmtime(h) for h in glob.glob(os.path.join(CSRC, "*.cuh")))
@@ -47,7 +55,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             print(out)
         if p.returncode != 0:
             raise RuntimeError(f"nvcc failed on {src}")
-        log = os.path.join(HERE, "build", os.path.basename(src) + ".ptxas.log")
+        log = os.path.join(BUILD_DIR, os.path.basename(src) + ".ptxas.log")
         with open(log, "w") as f:
             f.write(out)
     cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-lcudart_static", "-lpthread", "-ldl", "-lrt"]

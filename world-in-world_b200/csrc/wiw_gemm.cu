@@ -73,7 +73,11 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmArgs& g, int tile, in
     return t;
 }
 
-template <int CG, int GEGLU>      // GEGLU: 0 = plain epilogue, 2 = GEGLU epilogue (exact-erf GELU through the one-MUFU tanh fit, mul_gelu_tanhfit_f)
+// LEAN = 1 fixes at compile time what most layers of the model have anyway (no table, no activation, s_acc == 1, no aux operand,
+// per-warp stores, two staging buffers, no debug switches): the chunk loop of an epilogue warp is a serial chain of short latencies
+// (two warps per scheduler, nothing to hide them behind), and every runtime switch in it costs a constant-bank load + compare +
+// branch (profiles/r02_gemm_epilogue_phases_v2.txt: ~280 cycles to add a bias, ~170 to skip the release).
+template <int CG, int GEGLU, int LEAN>      // GEGLU: 0 = plain epilogue, 2 = GEGLU epilogue (exact-erf GELU through the one-MUFU tanh fit, mul_gelu_tanhfit_f)
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                  const __grid_constant__ CUtensorMap tm_out /* box = one warp's 32 rows x 32 channels */,
@@ -267,13 +271,32 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         int as = 0;
         uint32_t aph = 0;
         int ob = 0;                                    // this group's staging buffer (g.out_bufs per group, round robin)
-        const int nob = g.out_bufs;
+        const int nob = LEAN ? 2 : g.out_bufs;
+        const bool e_tab = !LEAN && g.tab != nullptr;
+        const int e_act = LEAN ? 0 : g.act;
+        const bool e_sacc = !LEAN && g.s_acc != 1.0f;
+        const bool e_aux = !LEAN && g.has_aux;
+        const bool e_res = g.has_res;
+        const bool e_loads = e_res || e_aux;
+        const int e_dbg = LEAN ? 0 : g.dbg;
+        const bool e_warp_store = LEAN ? true : (g.warp_store != 0);
+        const bool e_bias = g.bias != nullptr;
+        const float s_res = g.s_res;
+        const int wx0 = g.wx0[q], wy0 = g.wy0[q], wz0 = g.wz0[q];
         long long chunk_base = 0;                      // chunks consumed by this CTA before the current tile
         int chunks = 0;
-        const bool eprof = (g.dbg & 4) && blockIdx.x == 0 && warp == 3;
+        const bool eprof = (e_dbg & 4) && blockIdx.x == 0 && warp == 3;
         long long e_wait = 0;
-        long long eph[8] = {0, 0, 0, 0, 0, 0, 0, 0}, ech = 0, ets = 0;      // per-phase cycle sums: ld+bias | math | release | residual | wait_read | sts+fence | tma issue
+        // Per-phase cycle sums of the chunk loop (bias add | math | release | residual | wait_read | sts+fence | tma issue | tmem ld+wait)
+        // cost ~20 registers, so they exist only in a -DWIW_GEMM_PHASES build (WIW_BUILD_VARIANT=phases, scripts/perf_epilogue_phases.py).
+#ifdef WIW_GEMM_PHASES
+        long long eph[8] = {0, 0, 0, 0, 0, 0, 0, 0}, ech = 0, ets = 0;
 #define EPH(i) do { if (eprof) { const long long _n = clock64(); eph[i] += _n - ets; ets = _n; } } while (0)
+#define EPH_BEGIN() do { if (eprof) { ets = clock64(); ++ech; } } while (0)
+#else
+#define EPH(i) do { } while (0)
+#define EPH_BEGIN() do { } while (0)
+#endif
         const long long e_t0 = eprof ? clock64() : 0;
         for (int tile = first_tile; tile < g.total_tiles; tile += tile_step, chunk_base += chunks) {
             const TileCoord t = decode_tile<CG>(g, tile, cta_rank);
@@ -281,7 +304,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             const int out_c0 = t.n_tile * g.out_cols_per_tile;        // first output channel
             chunks = min(full_chunks, (g.out_total - out_c0) / kEpiCols);      // ragged last N-tile: padded columns are skipped
             const __half* tab_row = nullptr;
-            if (g.tab != nullptr) {
+            if (e_tab) {
                 const int x = t.x0 + (row % g.bx), y = t.y0 + (row / g.bx) % g.by, z = t.img + row / (g.bx * g.by);
                 long long grow = ((long long)z * g.dim_y + y) * g.dim_x + x;
                 if (grow < 0) grow = 0;
@@ -300,7 +323,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 if (lane == 0) { if (CG == 2) mbar_arrive_cluster(bar_tempty + 8 * as, 0); else mbar_arrive(bar_tempty + 8 * as); }
             }
             for (int j = grp; j < chunks; j += 2) {
-                if (eprof) { ets = clock64(); ++ech; }
+                EPH_BEGIN();
                 float v[kEpiCols];
                 uint32_t rg[kEpiCols];                              // gate half of a GEGLU tile
                 const int half_n = g.bn >> 1;
@@ -312,25 +335,26 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                     const int nb = acc_n0 + j * kEpiCols;
                     float4 b4[kEpiCols / 4];
                     uint4 tu[kEpiCols / 8];
-                    if (g.bias != nullptr) {
+                    if (e_bias) {
 #pragma unroll
                         for (int c = 0; c < kEpiCols / 4; ++c) b4[c] = __ldg(reinterpret_cast<const float4*>(g.bias + nb) + c);
                     }
-                    if (!GEGLU && tab_row != nullptr) {
+                    if (!GEGLU && e_tab) {
 #pragma unroll
                         for (int c = 0; c < kEpiCols / 8; ++c) tu[c] = __ldg(reinterpret_cast<const uint4*>(tab_row + nb) + c);
                     }
                     tmem_ld_wait();
+                    EPH(7);
                     if (GEGLU) tmem_ld_32x32b_x32(t_acc + half_n + j * kEpiCols, rg);
 #pragma unroll
                     for (int c = 0; c < kEpiCols; ++c) v[c] = __uint_as_float(r[c]);
-                    if (g.bias != nullptr) {
+                    if (e_bias) {
 #pragma unroll
                         for (int c = 0; c < kEpiCols; c += 4) {
                             v[c] += b4[c / 4].x; v[c + 1] += b4[c / 4].y; v[c + 2] += b4[c / 4].z; v[c + 3] += b4[c / 4].w;
                         }
                     }
-                    if (!GEGLU && tab_row != nullptr) {
+                    if (!GEGLU && e_tab) {
 #pragma unroll
                         for (int c = 0; c < kEpiCols; c += 8) {
                             const __half2* h = reinterpret_cast<const __half2*>(&tu[c / 8]);
@@ -341,13 +365,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                             }
                         }
                     }
-                    if (!GEGLU && g.act == 1) {
+                    if (!GEGLU && e_act == 1) {
 #pragma unroll
                         for (int c = 0; c < kEpiCols; ++c) v[c] = silu_f(v[c]);
-                    } else if (!GEGLU && g.act == 2) {           // exact-erf GELU (CLIP ViT-H MLP, transformers ACT2FN["gelu"])
+                    } else if (!GEGLU && e_act == 2) {           // exact-erf GELU (CLIP ViT-H MLP, transformers ACT2FN["gelu"])
 #pragma unroll
                         for (int c = 0; c < kEpiCols; ++c) v[c] = mul_gelu_tanhfit_f(1.0f, v[c]);
-                    } else if (!GEGLU && g.act == 3) {           // quick GELU x * sigmoid(1.702 x) (CLIPVisionConfig default)
+                    } else if (!GEGLU && e_act == 3) {           // quick GELU x * sigmoid(1.702 x) (CLIPVisionConfig default)
 #pragma unroll
                         for (int c = 0; c < kEpiCols; ++c) v[c] = quick_gelu_f(v[c]);
                     }
@@ -358,9 +382,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                     float4 b4[kEpiCols / 4];
 #pragma unroll
                     for (int c = 0; c < kEpiCols / 4; ++c)
-                        b4[c] = (g.bias != nullptr) ? __ldg(reinterpret_cast<const float4*>(g.bias + nb) + c) : make_float4(0, 0, 0, 0);
+                        b4[c] = e_bias ? __ldg(reinterpret_cast<const float4*>(g.bias + nb) + c) : make_float4(0, 0, 0, 0);
                     tmem_ld_wait();
-                    if (g.dbg & 8) {
+                    if (e_dbg & 8) {
 #pragma unroll
                         for (int c = 0; c < kEpiCols; ++c) v[c] *= __uint_as_float(rg[c]);
                     } else
@@ -379,18 +403,18 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                     __syncwarp();
                     if (lane == 0) { if (CG == 2) mbar_arrive_cluster(bar_tempty + 8 * as, 0); else mbar_arrive(bar_tempty + 8 * as); }
                 }
-                if (g.s_acc != 1.0f) {
+                if (e_sacc) {
 #pragma unroll
                     for (int c = 0; c < kEpiCols; ++c) v[c] *= g.s_acc;
                 }
                 EPH(2);
-                if (has_epi_loads) {
+                if (e_loads) {
                     const long long n = chunk_base + j;                       // global chunk index of this CTA
                     const int rs = int(n % g.res_slots);
                     const uint32_t rph = uint32_t(n / g.res_slots) & 1u;
                     mbar_wait(bar_rfull + 8 * rs, rph);
                     const uint8_t* gen = smem_raw + (res_base - smem_u32(smem_raw));
-                    if (g.has_res) {
+                    if (e_res) {
                         const uint8_t* p = gen + rs * kEpiChunkBytes + row_off;
 #pragma unroll
                         for (int c4 = 0; c4 < 4; ++c4) {
@@ -399,12 +423,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 #pragma unroll
                             for (int e = 0; e < 4; ++e) {
                                 const float2 f = __half22float2(h[e]);
-                                v[c4 * 8 + 2 * e] += g.s_res * f.x;
-                                v[c4 * 8 + 2 * e + 1] += g.s_res * f.y;
+                                v[c4 * 8 + 2 * e] += s_res * f.x;
+                                v[c4 * 8 + 2 * e + 1] += s_res * f.y;
                             }
                         }
                     }
-                    if (g.has_aux) {
+                    if (e_aux) {
                         const uint8_t* p = smem_raw + (aux_base - smem_u32(smem_raw)) + rs * kEpiChunkBytes + row_off;
 #pragma unroll
                         for (int c4 = 0; c4 < 4; ++c4) {
@@ -421,11 +445,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                     mbar_arrive(bar_rempty + 8 * rs);
                 }
                 EPH(3);
-                if (g.dbg & 16) { if (++ob == nob) ob = 0; continue; }
+                if (e_dbg & 16) { if (++ob == nob) ob = 0; continue; }
                 // The store issued two chunks ago by this group read the buffer we are about to overwrite:
                 // the leader waits until at most one of its bulk groups is still reading, then releases the group.
                 // the store issued `nob` chunks ago read the buffer about to be overwritten
-                if (g.warp_store) {
+                if (e_warp_store) {
                     if (elect_one()) { if (nob == 4) tma_store_wait_read<3>(); else tma_store_wait_read<1>(); }
                     __syncwarp();
                 } else {
@@ -446,11 +470,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 }
                 fence_proxy_async_smem();
                 EPH(5);
-                if (g.warp_store) {
+                if (e_warp_store) {
                     __syncwarp();                                  // the slab is complete and visible to the async proxy
                     if (elect_one()) {
                         tma_store_4d(&tm_out, out_base + (grp * nob + ob) * kEpiChunkBytes + q * (32 * 64), out_c0 + j * kEpiCols,
-                                     t.x0 + g.wx0[q], t.y0 + g.wy0[q], t.img + g.wz0[q]);
+                                     t.x0 + wx0, t.y0 + wy0, t.img + wz0);
                         tma_store_commit();
                     }
                     __syncwarp();
@@ -469,8 +493,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             }
             if (++as == 2) { as = 0; aph ^= 1; }
         }
+#ifdef WIW_GEMM_PHASES
         if (eprof && lane == 0) { for (int i = 0; i < 8; ++i) g_gemm_prof[8 + i] = eph[i]; g_gemm_prof[16] = ech; }
-        if (store_warp || g.warp_store) { if (elect_one()) tma_store_wait_all<0>(); __syncwarp(); }
+#endif
+        if (store_warp || e_warp_store) { if (elect_one()) tma_store_wait_all<0>(); __syncwarp(); }
         if (eprof && lane == 0) { g_gemm_prof[7] = clock64() - e_t0; g_gemm_prof[6] = e_wait; }
     }
 
@@ -595,33 +621,37 @@ static int launch_conv_gemm(const wiw_gemm_desc* d, cudaStream_t stream) {
 
     static unsigned long long attr_set = 0;
     if (first_call_on_device(&attr_set)) {
-        WIW_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
-        WIW_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
-        WIW_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
-        WIW_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+        const void* all[8] = {(const void*)conv_gemm_kernel<1, 0, 0>, (const void*)conv_gemm_kernel<2, 0, 0>, (const void*)conv_gemm_kernel<1, 2, 0>,
+                              (const void*)conv_gemm_kernel<2, 2, 0>, (const void*)conv_gemm_kernel<1, 0, 1>, (const void*)conv_gemm_kernel<2, 0, 1>,
+                              (const void*)conv_gemm_kernel<1, 2, 1>, (const void*)conv_gemm_kernel<2, 2, 1>};
+        for (const void* f : all) WIW_CHECK_CUDA(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
     }
+    static const int lean_env = getenv("WIW_GEMM_LEAN") ? atoi(getenv("WIW_GEMM_LEAN")) : 1;    // development aid for A/B runs
+    const bool lean = lean_env && !d->tab && d->act == 0 && d->s_acc == 1.0f && !d->aux && g.dbg == 0 && g.warp_store && g.out_bufs == 2;
+    using kernel_t = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const GemmArgs);
+    kernel_t kern;
+    if (cg == 1) kern = g.geglu ? (lean ? conv_gemm_kernel<1, 2, 1> : conv_gemm_kernel<1, 2, 0>) : (lean ? conv_gemm_kernel<1, 0, 1> : conv_gemm_kernel<1, 0, 0>);
+    else         kern = g.geglu ? (lean ? conv_gemm_kernel<2, 2, 1> : conv_gemm_kernel<2, 2, 0>) : (lean ? conv_gemm_kernel<2, 0, 1> : conv_gemm_kernel<2, 0, 0>);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
     if (cg == 1) {
         int grid = num_sms();
         if (grid > g.total_tiles) grid = g.total_tiles;
-        if (g.geglu) conv_gemm_kernel<1, 2><<<grid, kThreads, smem_bytes, stream>>>(tm_a, tm_b, tm_out, tm_res, tm_aux, g);
-        else conv_gemm_kernel<1, 0><<<grid, kThreads, smem_bytes, stream>>>(tm_a, tm_b, tm_out, tm_res, tm_aux, g);
+        cfg.gridDim = dim3(grid);
     } else {
         int pairs = num_sms() / 2;
         if (pairs > g.total_tiles) pairs = g.total_tiles;
-        cudaLaunchConfig_t cfg;
-        memset(&cfg, 0, sizeof(cfg));
         cfg.gridDim = dim3(2 * pairs);
-        cfg.blockDim = dim3(kThreads);
-        cfg.dynamicSmemBytes = smem_bytes;
-        cfg.stream = stream;
-        cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        if (g.geglu) WIW_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<2, 2>, tm_a, tm_b, tm_out, tm_res, tm_aux, g));
-        else WIW_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<2, 0>, tm_a, tm_b, tm_out, tm_res, tm_aux, g));
     }
+    WIW_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tm_a, tm_b, tm_out, tm_res, tm_aux, g));
     WIW_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
