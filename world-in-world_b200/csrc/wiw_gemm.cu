@@ -73,8 +73,8 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmArgs& g, int tile, in
     return t;
 }
 
-// LEAN = 1 fixes at compile time what most layers of the model have anyway (no table, no activation, s_acc == 1, no aux operand,
-// per-warp stores, two staging buffers, no debug switches): the chunk loop of an epilogue warp is a serial chain of short latencies
+// LEAN = 1 fixes at compile time what most layers of the model have anyway (no activation, no aux operand, per-warp stores,
+// two staging buffers, four residual slots, no debug switches): the chunk loop of an epilogue warp is a serial chain of short latencies
 // (two warps per scheduler, nothing to hide them behind), and every runtime switch in it costs a constant-bank load + compare +
 // branch (profiles/r02_gemm_epilogue_phases_v2.txt: ~280 cycles to add a bias, ~170 to skip the release).
 template <int CG, int GEGLU, int LEAN>      // GEGLU: 0 = plain epilogue, 2 = GEGLU epilogue (exact-erf GELU through the one-MUFU tanh fit, mul_gelu_tanhfit_f)
@@ -272,18 +272,21 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         uint32_t aph = 0;
         int ob = 0;                                    // this group's staging buffer (g.out_bufs per group, round robin)
         const int nob = LEAN ? 2 : g.out_bufs;
-        const bool e_tab = !LEAN && g.tab != nullptr;
+        const bool e_tab = g.tab != nullptr;
         const int e_act = LEAN ? 0 : g.act;
-        const bool e_sacc = !LEAN && g.s_acc != 1.0f;
+        const float s_acc = g.s_acc;
+        const bool e_sacc = s_acc != 1.0f;
+        const int res_slots = LEAN ? 4 : g.res_slots;
+        const int res_shift = (res_slots == 8) ? 3 : 2;
         const bool e_aux = !LEAN && g.has_aux;
         const bool e_res = g.has_res;
         const bool e_loads = e_res || e_aux;
-        const int e_dbg = LEAN ? 0 : g.dbg;
+        const int e_dbg = LEAN ? (g.dbg & 4) : g.dbg;      // bit 4 = profile counters, read once per kernel
         const bool e_warp_store = LEAN ? true : (g.warp_store != 0);
         const bool e_bias = g.bias != nullptr;
         const float s_res = g.s_res;
         const int wx0 = g.wx0[q], wy0 = g.wy0[q], wz0 = g.wz0[q];
-        long long chunk_base = 0;                      // chunks consumed by this CTA before the current tile
+        uint32_t chunk_base = 0;                       // chunks consumed by this CTA before the current tile (mod 2^32: only its low bits are used)
         int chunks = 0;
         const bool eprof = (e_dbg & 4) && blockIdx.x == 0 && warp == 3;
         long long e_wait = 0;
@@ -342,6 +345,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                     if (!GEGLU && e_tab) {
 #pragma unroll
                         for (int c = 0; c < kEpiCols / 8; ++c) tu[c] = __ldg(reinterpret_cast<const uint4*>(tab_row + nb) + c);
+                    }
+                    if (LEAN) {
+                        // the staging buffer this chunk will overwrite was read by the store issued two chunks ago: waiting for
+                        // that read here, under the TMEM load's latency, takes it off the serial chain
+                        if (elect_one()) tma_store_wait_read<1>();
+                        __syncwarp();
                     }
                     tmem_ld_wait();
                     EPH(7);
@@ -405,13 +414,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 }
                 if (e_sacc) {
 #pragma unroll
-                    for (int c = 0; c < kEpiCols; ++c) v[c] *= g.s_acc;
+                    for (int c = 0; c < kEpiCols; ++c) v[c] *= s_acc;
                 }
                 EPH(2);
                 if (e_loads) {
-                    const long long n = chunk_base + j;                       // global chunk index of this CTA
-                    const int rs = int(n % g.res_slots);
-                    const uint32_t rph = uint32_t(n / g.res_slots) & 1u;
+                    const uint32_t n = chunk_base + uint32_t(j);              // global chunk index of this CTA (res_slots is 4 or 8: mask and shift, no division)
+                    const int rs = int(n & uint32_t(res_slots - 1));
+                    const uint32_t rph = (n >> res_shift) & 1u;
                     mbar_wait(bar_rfull + 8 * rs, rph);
                     const uint8_t* gen = smem_raw + (res_base - smem_u32(smem_raw));
                     if (e_res) {
@@ -449,7 +458,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 // The store issued two chunks ago by this group read the buffer we are about to overwrite:
                 // the leader waits until at most one of its bulk groups is still reading, then releases the group.
                 // the store issued `nob` chunks ago read the buffer about to be overwritten
-                if (e_warp_store) {
+                if (LEAN) {
+                    // waited above
+                } else if (e_warp_store) {
                     if (elect_one()) { if (nob == 4) tma_store_wait_read<3>(); else tma_store_wait_read<1>(); }
                     __syncwarp();
                 } else {
@@ -627,7 +638,7 @@ static int launch_conv_gemm(const wiw_gemm_desc* d, cudaStream_t stream) {
         for (const void* f : all) WIW_CHECK_CUDA(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
     }
     static const int lean_env = getenv("WIW_GEMM_LEAN") ? atoi(getenv("WIW_GEMM_LEAN")) : 1;    // development aid for A/B runs
-    const bool lean = lean_env && !d->tab && d->act == 0 && d->s_acc == 1.0f && !d->aux && g.dbg == 0 && g.warp_store && g.out_bufs == 2;
+    const bool lean = lean_env && d->act == 0 && !d->aux && (g.dbg & ~4) == 0 && g.warp_store && g.out_bufs == 2 && g.res_slots == 4;
     using kernel_t = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const GemmArgs);
     kernel_t kern;
     if (cg == 1) kern = g.geglu ? (lean ? conv_gemm_kernel<1, 2, 1> : conv_gemm_kernel<1, 2, 0>) : (lean ? conv_gemm_kernel<1, 0, 1> : conv_gemm_kernel<1, 0, 0>);
