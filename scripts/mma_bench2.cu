@@ -161,6 +161,50 @@ __global__ void __launch_bounds__(512, 1) tmem_rw_bench(int warps_active, int re
     if (threadIdx.x < 32) { tc_fence_after(); tmem_dealloc(tmem, 512); }
 }
 
+// ---------------------------------------------------------------- tcgen05.ld LATENCY: one x32 load, wait, consume -- the epilogue's pattern
+__global__ void __launch_bounds__(512, 1) tmem_lat_bench(int warps_active, int reps, int loads, long long* out) {
+    __shared__ uint32_t slot;
+    if (threadIdx.x < 32) { tmem_alloc(smem_u32(&slot), 512); tmem_relinquish(); }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = slot;
+    const int warp = threadIdx.x >> 5;
+    uint32_t acc = 0;
+    __syncthreads();
+    const long long t0 = clock64();
+    if (warp < warps_active) {
+        const uint32_t t = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * 64);
+        for (int it = 0; it < reps; ++it) {
+            uint32_t r[32], r2[32];
+            tmem_ld_32x32b_x32(t + (acc & 1u), r);                 // address depends on the previous result: no overlap between iterations
+            if (loads == 2) tmem_ld_32x32b_x32(t + 32 + (acc & 1u), r2);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) acc += r[i];
+            if (loads == 2) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) acc += r2[i];
+            }
+        }
+    }
+    const long long t1 = clock64();
+    __syncthreads();
+    if (acc == 0x12345678u) out[3] = acc;
+    if (threadIdx.x == 0 && blockIdx.x == 0) out[0] = t1 - t0;
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x < 32) { tc_fence_after(); tmem_dealloc(tmem, 512); }
+}
+static void run_tmem_lat(int warps, int loads) {
+    const int reps = 256;
+    tmem_lat_bench<<<148, 512>>>(warps, reps, loads, g_out);
+    cudaError_t e = cudaDeviceSynchronize();
+    long long h = 0; cudaMemcpy(&h, g_out, 8, cudaMemcpyDeviceToHost);
+    printf("tcgen05.ld latency, %d x32 load(s) + wait + consume, %2d warps/SM: %6.1f cycles per iteration  %s\n", loads, warps,
+           double(h) / reps, e ? cudaGetErrorString(e) : "");
+}
+
 static void run_tmem(int store, int warps) {
     const int reps = 256;
     if (store) tmem_rw_bench<1><<<148, 512>>>(warps, reps, g_out); else tmem_rw_bench<0><<<148, 512>>>(warps, reps, g_out);
@@ -190,6 +234,7 @@ int main() {
     bad |= run<1, 128, 64, 0, 4, 1>(); bad |= run<1, 128, 80, 0, 4, 1>(); bad |= run<1, 128, 64, 1, 4, 1>(); bad |= run<1, 128, 80, 1, 4, 1>();
     bad |= run<1, 128, 128, 1, 2, 1>();
     for (int w : {1, 4, 8, 16}) run_tmem(0, w);
+    for (int w : {1, 4, 8}) { run_tmem_lat(w, 1); run_tmem_lat(w, 2); }
     for (int w : {1, 4, 8, 16}) run_tmem(1, w);
     return bad;
 }

@@ -24,7 +24,7 @@ def report(tag, fn, flop):
     ch = max(v[16], 1)
     print(f"{tag}: {ms:.4f} ms {flop / ms / 1e9:.0f} TFLOP/s | MMA warp: total {v[0]} cyc, wait data {v[1]}, wait acc-empty {v[2]} | epilogue warp: total {v[7]}, "
           f"wait acc-full {v[6]}, chunks {v[16]}")
-    print("      cycles per chunk: " + ", ".join(f"{n} {v[8 + i] / ch:.0f}" for i, n in enumerate(names)) + f" | sum {sum(v[8:16]) / ch:.0f}", flush=True)
+    print("      cycles per chunk: " + ", ".join(f"{n} {v[8 + i] / ch:.0f}" for i, n in enumerate(names)) + f", first use of chunk a {v[17] / ch:.0f}, of chunk b {v[18] / ch:.0f} | sum {(sum(v[8:16]) + v[17] + v[18]) / ch:.0f}", flush=True)
 
 
 m, c = 258048, 320

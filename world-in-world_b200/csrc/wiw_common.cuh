@@ -75,10 +75,16 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 }
 // Spin on the phase parity.  A kernel that waits ~2 s has a protocol bug: trap instead of
 // hanging the device.
+// (No function call here: a call anywhere in a kernel makes ptxas ignore the per-role register budgets of setmaxnreg --
+// measured with a toy kernel, everything was allocated under the smallest budget.  -DWIW_TRAP_PRINTF brings the message back.)
+#ifdef WIW_TRAP_PRINTF
 static __device__ __noinline__ void mbar_timeout_trap(uint32_t bar) {
     printf("wiw: mbarrier timeout (block %d thread %d bar 0x%x)\n", blockIdx.x, threadIdx.x, bar);
     __trap();
 }
+#else
+__device__ __forceinline__ void mbar_timeout_trap(uint32_t) { asm volatile("trap;"); }
+#endif
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t done = 0;
     uint32_t spins = 0;

@@ -28,7 +28,10 @@ constexpr int kEpiChunkBytes = kBlockM * kEpiCols * 2;   // 8 KB
 constexpr int kMaxOutBufs = 8;                 // staging chunks: 2 or 4 per epilogue group (GemmArgs::out_bufs)
 constexpr int kMaxResSlots = 8;                // residual / aux chunk slots: GemmArgs::res_slots (4 or 8)
 constexpr int kMaxStages = 8;
-constexpr int kThreads = 11 * 32;              // TMA, MMA, epilogue loader, 2 x 4 epilogue warps
+constexpr int kThreads = 12 * 32;              // warpgroup 0: TMA, MMA, epilogue loader, (idle); warpgroups 1-2: 2 x 4 epilogue warps
+constexpr int kBiasStageBytes = 2 * 2 * 512;    // lean epilogue: per epilogue group, two tiles' worth (accumulator-stage parity) of bias values
+constexpr int kRegsProducer = 40;              // setmaxnreg budgets: 128 * 40 + 256 * 232 = 64512 = 384 * 168 (what the launch allocates)
+constexpr int kRegsEpilogue = 232;
 constexpr int kSmemBudget = 227 * 1024;
 
 struct GemmArgs {
@@ -73,6 +76,98 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmArgs& g, int tile, in
     return t;
 }
 
+// ----------------------------------------------------------------------------- lean-epilogue pieces (one 32-column chunk of one row per thread)
+// The epilogue warps are ISSUE-bound (two warps per scheduler, ~350 instructions per pair of chunks): all fp32 arithmetic is done
+// on register pairs with the packed f32x2 forms (FADD2 / FMUL2 / FFMA2: same pipe time as the scalar forms, half the issue slots --
+// scripts/ffma2_bench.cu).  Results are bit-identical to the scalar code: same operations, same rounding, two lanes per instruction.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float a, float b) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ f32x2 pk2u(uint32_t a, uint32_t b) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(a), "r"(b)); return r; }
+__device__ __forceinline__ void upk2(f32x2 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f32x2 half2_to_f32x2(const __half2 h) { const float2 f = __half22float2(h); return pk2(f.x, f.y); }
+constexpr int kEpiPairs = kEpiCols / 2;
+
+// bias: 32 floats in shared memory (the group's copy, staged once per tile); tab: this row's 32 fp16 table values, already in registers
+__device__ __forceinline__ void lean_bias_tab(f32x2 (&v)[kEpiPairs], const uint32_t (&r)[kEpiCols], const float* bias_smem, bool has_tab,
+                                              const uint4 (&tu)[kEpiCols / 8]) {
+#pragma unroll
+    for (int c = 0; c < kEpiPairs; ++c) v[c] = pk2u(r[2 * c], r[2 * c + 1]);
+    if (bias_smem != nullptr) {
+#pragma unroll
+        for (int c = 0; c < kEpiPairs; c += 2) {
+            const ulonglong2 b = *reinterpret_cast<const ulonglong2*>(bias_smem + 2 * c);
+            v[c] = add2(v[c], b.x); v[c + 1] = add2(v[c + 1], b.y);
+        }
+    }
+    if (has_tab) {
+#pragma unroll
+        for (int c = 0; c < kEpiCols / 8; ++c) {
+            const __half2* h = reinterpret_cast<const __half2*>(&tu[c]);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) v[4 * c + e] = add2(v[4 * c + e], half2_to_f32x2(h[e]));
+        }
+    }
+}
+// v *= gelu(gate + bias) with mul_gelu_tanhfit_f's polynomial, evaluated in y = x / 2 so that the halving costs nothing: the staged
+// gate bias is ALREADY halved (power-of-two scalings commute with rounding, so every intermediate equals the scalar code's):
+//   y = 0.5 g + 0.5 b;  tanh argument x p(x^2) = y q(y^2) with q(s) = 2 c0 + 8 c1 s + 32 c2 s^2;  v * 0.5 x = v y
+__device__ __forceinline__ void lean_geglu(f32x2 (&v)[kEpiPairs], const uint32_t (&rg)[kEpiCols], const float* half_bias_smem) {
+    const f32x2 half = pk2(0.5f, 0.5f);
+    const f32x2 q2 = pk2(32.0f * -3.58549415e-4f, 32.0f * -3.58549415e-4f), q1 = pk2(8.0f * 3.70488970e-2f, 8.0f * 3.70488970e-2f),
+                q0 = pk2(2.0f * 7.97460674e-1f, 2.0f * 7.97460674e-1f);
+#pragma unroll
+    for (int c = 0; c < kEpiPairs; c += 2) {
+        ulonglong2 hb = make_ulonglong2(0ull, 0ull);
+        if (half_bias_smem != nullptr) hb = *reinterpret_cast<const ulonglong2*>(half_bias_smem + 2 * c);
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const f32x2 y = fma2(pk2u(rg[2 * (c + e)], rg[2 * (c + e) + 1]), half, e ? hb.y : hb.x);
+            const f32x2 y2 = mul2(y, y);
+            f32x2 p = fma2(y2, q2, q1);
+            p = fma2(p, y2, q0);
+            float a0, a1, t0, t1;
+            upk2(mul2(y, p), a0, a1);
+            asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(a0));
+            asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(a1));
+            const f32x2 w = mul2(v[c + e], y);
+            v[c + e] = fma2(w, pk2(t0, t1), w);
+        }
+    }
+}
+// residual chunk n of this CTA sits in slot n % 4 (phase bit (n / 4) & 1), written by the loader warp
+__device__ __forceinline__ void lean_residual(f32x2 (&v)[kEpiPairs], const uint8_t* slots_row, uint32_t n, uint32_t bar_rfull,
+                                              uint32_t bar_rempty, float s_res, uint32_t sw) {
+    const uint32_t rs = n & 3u;
+    mbar_wait(bar_rfull + 8 * rs, (n >> 2) & 1u);
+    const uint8_t* p = slots_row + rs * kEpiChunkBytes;
+    const f32x2 s2 = pk2(s_res, s_res);
+#pragma unroll
+    for (int c4 = 0; c4 < 4; ++c4) {
+        const uint4 u = *reinterpret_cast<const uint4*>(p + ((uint32_t(c4) ^ sw) << 4));
+        const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) v[c4 * 4 + e] = fma2(s2, half2_to_f32x2(h[e]), v[c4 * 4 + e]);
+    }
+    mbar_arrive(bar_rempty + 8 * rs);
+}
+__device__ __forceinline__ void lean_stage(uint8_t* p, const f32x2 (&v)[kEpiPairs], uint32_t sw) {
+#pragma unroll
+    for (int c4 = 0; c4 < 4; ++c4) {
+        uint4 u;
+        __half2* h = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            float a, b;
+            upk2(v[c4 * 4 + e], a, b);
+            h[e] = __floats2half2_rn(a, b);
+        }
+        *reinterpret_cast<uint4*>(p + ((uint32_t(c4) ^ sw) << 4)) = u;
+    }
+}
+
 // LEAN = 1 fixes at compile time what most layers of the model have anyway (no activation, no aux operand, per-warp stores,
 // two staging buffers, four residual slots, no debug switches): the chunk loop of an epilogue warp is a serial chain of short latencies
 // (two warps per scheduler, nothing to hide them behind), and every runtime switch in it costs a constant-bank load + compare +
@@ -85,7 +180,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                  const __grid_constant__ GemmArgs g) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // carve: [stages x (A 16 KB | B bn*128)] [out bufs] [res slots] [aux slots] [barriers]
-    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    // The dynamic window is declared 1024-byte aligned (SWIZZLE_128B atoms) and the host budgets NO slack for a run-time round-up:
+    // the 1 KB it used to cost is what keeps the 6th pipeline stage next to the bias copies.  A base that is not aligned traps.
+    const uint32_t smem_base = smem_u32(smem_raw);
+    if ((smem_base & 1023u) != 0u) asm volatile("trap;");
     const uint32_t a_bytes = kBlockM * kBlockK * 2;
     const uint32_t b_bytes = (g.bn / CG) * kBlockK * 2;          // with cta_group::2 each CTA stages half of the N-tile
     const uint32_t stage_bytes = a_bytes + b_bytes;
@@ -102,6 +200,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     const uint32_t bar_rempty = bar_rfull + 8 * kMaxResSlots;   // [kMaxResSlots]
     const uint32_t tmem_slot = bar_rempty + 8 * kMaxResSlots;   // uint32
     uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+    // lean epilogue: [group][accumulator stage][128 floats] bias values of the chunks the group handles in a tile (kBiasStageBytes)
+    float* const bias_stage = reinterpret_cast<float*>(smem_raw + (((tmem_slot + 16 + 15) & ~15u) - smem_u32(smem_raw)));
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -140,10 +240,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     if (CG == 2) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
+    // The three producer warps need few registers; the epilogue warps' chunk loop is a serial latency chain that only more
+    // independent work per warp (two chunks in flight, held in registers) shortens.  Rebalance the register file by warpgroup.
+    // (setmaxnreg sits INSIDE each role's branch: ptxas budgets code reachable from both settings with the smaller one.)
     const uint32_t acc_stride = (g.bn <= 32) ? 32 : (g.bn <= 64 ? 64 : (g.bn <= 128 ? 128 : 256));
 
     if (warp == 0) {
         // ================================ TMA producer ================================
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsProducer));
         // The whole warp runs the loop (warp-uniform control flow) and ONE elected lane issues: a TMA / tcgen05
         // instruction reached under a divergent `lane == 0` branch is wrapped by ptxas in an ELECT + BRA.U.ANY
         // serialisation loop with its operands moved through R2UR, which costs ~100 cycles per instruction
@@ -186,6 +290,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         }
         if (prof && lane == 0) { g_gemm_prof[4] = clock64() - p_t0; g_gemm_prof[5] = p_wait; }
     } else if (warp == 1) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsProducer));
         // ================================ MMA issuer ================================
         if (cta_rank == 0) {                              // the leader CTA issues the MMAs of the pair
             const uint32_t idesc = make_idesc_f16(g.bn, 0, 0, 128 * CG);
@@ -233,6 +338,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             if (prof && lane == 0) { g_gemm_prof[0] = clock64() - m_t0; g_gemm_prof[1] = m_wfull; g_gemm_prof[2] = m_wacc; g_gemm_prof[3] = m_steps; }
         }
     } else if (warp == 2) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsProducer));
         // ================================ epilogue loader ================================
         if (has_epi_loads) {
             const int full_chunks = g.out_cols_per_tile / kEpiCols;
@@ -255,15 +361,18 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 }
             }
         }
+    } else if (warp == 3) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsProducer));      // idle: completes warpgroup 0 for setmaxnreg
     } else {
-        // ================================ epilogue (warps 3..10, two groups of 4) ================================
+        // ================================ epilogue (warps 4..11, two groups of 4) ================================
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsEpilogue));
         // Group grp handles the 32-column chunks j with j % 2 == grp; both groups read the same TMEM lanes
         // (a warp may only touch lane quadrant warp % 4).  Two warps per SM sub-partition hide each other's
         // TMEM-load / barrier / store latency.
-        const int grp = (warp - 3) >> 2;
+        const int grp = (warp - 4) >> 2;
         const int q = warp & 3;                        // TMEM lane quadrant this warp may access
         const int row = q * 32 + lane;                 // row of the 128-row tile == TMEM lane
-        const bool store_warp = (((warp - 3) & 3) == 0);   // its elected lane owns the group's bulk-store groups (elect.sync is deterministic)
+        const bool store_warp = (((warp - 4) & 3) == 0);   // its elected lane owns the group's bulk-store groups (elect.sync is deterministic)
         const int full_chunks = g.out_cols_per_tile / kEpiCols;
         const uint32_t sw = (uint32_t(row) >> 1) & 3u;  // SWIZZLE_64B: 16-B chunk index ^= (row>>1)&3
         const uint32_t row_off = uint32_t(row) * 64u;
@@ -288,12 +397,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         const int wx0 = g.wx0[q], wy0 = g.wy0[q], wz0 = g.wz0[q];
         uint32_t chunk_base = 0;                       // chunks consumed by this CTA before the current tile (mod 2^32: only its low bits are used)
         int chunks = 0;
-        const bool eprof = (e_dbg & 4) && blockIdx.x == 0 && warp == 3;
+        const bool eprof = (e_dbg & 4) && blockIdx.x == 0 && warp == 4;
         long long e_wait = 0;
         // Per-phase cycle sums of the chunk loop (bias add | math | release | residual | wait_read | sts+fence | tma issue | tmem ld+wait)
         // cost ~20 registers, so they exist only in a -DWIW_GEMM_PHASES build (WIW_BUILD_VARIANT=phases, scripts/perf_epilogue_phases.py).
 #ifdef WIW_GEMM_PHASES
-        long long eph[8] = {0, 0, 0, 0, 0, 0, 0, 0}, ech = 0, ets = 0;
+        long long eph[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, ech = 0, ets = 0;      // [8], [9]: first use of the first / second accumulator chunk (lean loop)
 #define EPH(i) do { if (eprof) { const long long _n = clock64(); eph[i] += _n - ets; ets = _n; } } while (0)
 #define EPH_BEGIN() do { if (eprof) { ets = clock64(); ++ech; } } while (0)
 #else
@@ -314,10 +423,28 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 int gi = int((grow / g.tab_div) % g.tab_mod);
                 tab_row = g.tab + (size_t)gi * g.tab_stride;
             }
+            // Bias values of this group's chunks: lane l fetches float4 (l & 7) of slot (l >> 3) -- plain tiles, slot ci = chunk
+            // grp + 2 ci (<= 4 per group); GEGLU tiles (<= 2 chunks per group), slots 0-1 = value-half, slots 2-3 = gate-half bias of
+            // chunks grp, grp + 2.  The load is issued before the wait for the accumulator (its latency is never on the chunk loop's
+            // chain) and stored after it: the four warps of a group write the SAME values to the group's copy for this accumulator
+            // stage, and a full barrier phase on that stage means every warp has finished reading the copy of two tiles ago.
+            float* const wbias = bias_stage + (grp * 2 + as) * 128;
+            float4 bias_v = make_float4(0, 0, 0, 0);
+            if (LEAN && e_bias) {
+                const int ci = lane >> 3, part = lane & 7;
+                const int j = GEGLU ? grp + 2 * (ci & 1) : grp + 2 * ci;
+                const int off = (GEGLU && ci >= 2) ? (g.bn >> 1) : 0;
+                if (j < chunks) bias_v = __ldg(reinterpret_cast<const float4*>(g.bias + acc_n0 + off + j * kEpiCols) + part);
+                if (GEGLU && ci >= 2) { bias_v.x *= 0.5f; bias_v.y *= 0.5f; bias_v.z *= 0.5f; bias_v.w *= 0.5f; }      // lean_geglu works in x / 2
+            }
             const long long e0 = (eprof) ? clock64() : 0;
             mbar_wait(bar_tfull + 8 * as, aph);
             if (eprof) e_wait += clock64() - e0;
             tc_fence_after();
+            if (LEAN && e_bias) {
+                *reinterpret_cast<float4*>(wbias + lane * 4) = bias_v;
+                __syncwarp();
+            }
             const uint32_t t_acc = tmem_base + as * acc_stride + (uint32_t(q * 32) << 16);
             const int last_j = ((chunks - 1 - grp) >= 0) ? (grp + 2 * ((chunks - 1 - grp) / 2)) : -1;
             if (last_j < 0) {                          // nothing to do for this group in this tile
@@ -325,6 +452,89 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 __syncwarp();
                 if (lane == 0) { if (CG == 2) mbar_arrive_cluster(bar_tempty + 8 * as, 0); else mbar_arrive(bar_tempty + 8 * as); }
             }
+            if (LEAN) {
+                // ---- lean epilogue: TWO chunks of this group (j0, j0 + 2) in flight per iteration.  An epilogue warp's chunk is a
+                // serial chain (tcgen05.ld -> wait -> bias -> [GELU] -> residual -> st.shared -> proxy fence -> bulk store) with one
+                // other warp on its scheduler to hide it; two chunks held in registers (setmaxnreg gives the room) overlap the
+                // TMEM loads, share ONE fence and ONE bulk-group commit, and halve the per-chunk cost of the serial parts.
+                const int half_n = g.bn >> 1;
+                uint8_t* const stage = smem_raw + (out_base - smem_u32(smem_raw)) + (grp * 2) * kEpiChunkBytes + row_off;
+                for (int j0 = grp; j0 < chunks; j0 += 4) {
+                    EPH_BEGIN();
+                    const int j1 = j0 + 2;
+                    const bool two = j1 < chunks;
+                    uint32_t ra[kEpiCols], rb[kEpiCols];
+                    f32x2 va[kEpiPairs], vb[kEpiPairs];
+                    tmem_ld_32x32b_x32(t_acc + j0 * kEpiCols, ra);
+                    if (two) tmem_ld_32x32b_x32(t_acc + j1 * kEpiCols, rb);
+                    const int ci0 = (j0 - grp) >> 1;               // bias slot of chunk j0 (j1: the next one)
+                    const bool has_tab = !GEGLU && e_tab;
+                    uint4 ta[kEpiCols / 8], tb[kEpiCols / 8];
+                    if (has_tab) {                                 // per-row table values: issued under the TMEM load
+#pragma unroll
+                        for (int c = 0; c < kEpiCols / 8; ++c) {
+                            ta[c] = __ldg(reinterpret_cast<const uint4*>(tab_row + acc_n0 + j0 * kEpiCols) + c);
+                            if (two) tb[c] = __ldg(reinterpret_cast<const uint4*>(tab_row + acc_n0 + j1 * kEpiCols) + c);
+                        }
+                    }
+                    tmem_ld_wait();
+                    EPH(7);
+#ifdef WIW_GEMM_PHASES
+                    if (eprof) {       // how long until the loaded registers can actually be read (the wait above does not stall the clock read)
+                        if (ra[0] == 0x7fc12345u) ++ech;
+                        EPH(8);
+                        if (two && rb[31] == 0x7fc12345u) ++ech;
+                        EPH(9);
+                    }
+#endif
+                    lean_bias_tab(va, ra, e_bias ? wbias + ci0 * kEpiCols : nullptr, has_tab, ta);
+                    if (two) lean_bias_tab(vb, rb, e_bias ? wbias + (ci0 + 1) * kEpiCols : nullptr, has_tab, tb);
+                    EPH(0);
+                    if (GEGLU) {
+                        tmem_ld_32x32b_x32(t_acc + half_n + j0 * kEpiCols, ra);
+                        if (two) tmem_ld_32x32b_x32(t_acc + half_n + j1 * kEpiCols, rb);
+                        tmem_ld_wait();
+                        lean_geglu(va, ra, e_bias ? wbias + 2 * kEpiCols : nullptr);
+                        if (two) lean_geglu(vb, rb, e_bias ? wbias + 3 * kEpiCols : nullptr);
+                    }
+                    EPH(1);
+                    if (j0 + 4 >= chunks) {
+                        // this group's TMEM reads of the accumulator stage are done: hand it back to the MMA warp
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) { if (CG == 2) mbar_arrive_cluster(bar_tempty + 8 * as, 0); else mbar_arrive(bar_tempty + 8 * as); }
+                    }
+                    if (e_sacc) {
+                        const f32x2 sa = pk2(s_acc, s_acc);
+#pragma unroll
+                        for (int c = 0; c < kEpiPairs; ++c) { va[c] = mul2(va[c], sa); vb[c] = mul2(vb[c], sa); }
+                    }
+                    EPH(2);
+                    if (e_res) {
+                        const uint8_t* gen = smem_raw + (res_base - smem_u32(smem_raw)) + row_off;
+                        lean_residual(va, gen, chunk_base + uint32_t(j0), bar_rfull, bar_rempty, s_res, sw);
+                        if (two) lean_residual(vb, gen, chunk_base + uint32_t(j1), bar_rfull, bar_rempty, s_res, sw);
+                    }
+                    EPH(3);
+                    // both staging buffers of the group are rewritten: every earlier bulk store of this warp must have read its slab
+                    if (elect_one()) tma_store_wait_read<0>();
+                    __syncwarp();
+                    EPH(4);
+                    lean_stage(stage, va, sw);
+                    if (two) lean_stage(stage + kEpiChunkBytes, vb, sw);
+                    fence_proxy_async_smem();
+                    EPH(5);
+                    __syncwarp();                                  // the slabs are complete and visible to the async proxy
+                    if (elect_one()) {
+                        const uint32_t src = out_base + (grp * 2) * kEpiChunkBytes + q * (32 * 64);
+                        tma_store_4d(&tm_out, src, out_c0 + j0 * kEpiCols, t.x0 + wx0, t.y0 + wy0, t.img + wz0);
+                        if (two) tma_store_4d(&tm_out, src + kEpiChunkBytes, out_c0 + j1 * kEpiCols, t.x0 + wx0, t.y0 + wy0, t.img + wz0);
+                        tma_store_commit();
+                    }
+                    __syncwarp();
+                    EPH(6);
+                }
+            } else
             for (int j = grp; j < chunks; j += 2) {
                 EPH_BEGIN();
                 float v[kEpiCols];
@@ -505,7 +715,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             if (++as == 2) { as = 0; aph ^= 1; }
         }
 #ifdef WIW_GEMM_PHASES
-        if (eprof && lane == 0) { for (int i = 0; i < 8; ++i) g_gemm_prof[8 + i] = eph[i]; g_gemm_prof[16] = ech; }
+        if (eprof && lane == 0) { for (int i = 0; i < 8; ++i) g_gemm_prof[8 + i] = eph[i]; g_gemm_prof[16] = ech; g_gemm_prof[17] = eph[8]; g_gemm_prof[18] = eph[9]; }
 #endif
         if (store_warp || e_warp_store) { if (elect_one()) tma_store_wait_all<0>(); __syncwarp(); }
         if (eprof && lane == 0) { g_gemm_prof[7] = clock64() - e_t0; g_gemm_prof[6] = e_wait; }
@@ -593,11 +803,11 @@ static int launch_conv_gemm(const wiw_gemm_desc* d, cudaStream_t stream) {
     g.res_slots = 4;
     {
         const int sb = kBlockM * kBlockK * 2 + (g.bn / cg) * kBlockK * 2;
-        const int fixed8 = 1024 + 2 * g.out_bufs * kEpiChunkBytes + 8 * kEpiChunkBytes + 512;
+        const int fixed8 = 2 * g.out_bufs * kEpiChunkBytes + 8 * kEpiChunkBytes + 512 + kBiasStageBytes;
         if (rslots_env == 8 && (g.has_res != g.has_aux) && (kSmemBudget - fixed8) / sb >= 4) g.res_slots = 8;
     }
-    const int fixed = 1024 /*align slack*/ + 2 * g.out_bufs * kEpiChunkBytes + (g.has_res ? g.res_slots * kEpiChunkBytes : 0) +
-                      (g.has_aux ? g.res_slots * kEpiChunkBytes : 0) + 512 /*barriers*/;
+    const int fixed = 2 * g.out_bufs * kEpiChunkBytes + (g.has_res ? g.res_slots * kEpiChunkBytes : 0) +
+                      (g.has_aux ? g.res_slots * kEpiChunkBytes : 0) + 512 /*barriers*/ + kBiasStageBytes;
     int stages = (kSmemBudget - fixed) / stage_bytes;
     if (stages > kMaxStages) stages = kMaxStages;
     WIW_REQUIRE(stages >= 2, "not enough shared memory for 2 pipeline stages");
@@ -638,7 +848,7 @@ static int launch_conv_gemm(const wiw_gemm_desc* d, cudaStream_t stream) {
         for (const void* f : all) WIW_CHECK_CUDA(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
     }
     static const int lean_env = getenv("WIW_GEMM_LEAN") ? atoi(getenv("WIW_GEMM_LEAN")) : 1;    // development aid for A/B runs
-    const bool lean = lean_env && d->act == 0 && !d->aux && (g.dbg & ~4) == 0 && g.warp_store && g.out_bufs == 2 && g.res_slots == 4;
+    const bool lean = lean_env && d->act == 0 && !d->aux && (g.dbg & ~7) == 0 && g.warp_store && g.out_bufs == 2 && g.res_slots == 4;
     using kernel_t = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const GemmArgs);
     kernel_t kern;
     if (cg == 1) kern = g.geglu ? (lean ? conv_gemm_kernel<1, 2, 1> : conv_gemm_kernel<1, 2, 0>) : (lean ? conv_gemm_kernel<1, 0, 1> : conv_gemm_kernel<1, 0, 0>);
