@@ -152,3 +152,36 @@ def test_many_tiles_persistent_loop():
     y = ops.linear(x, gw, res=res)
     ref = F.linear(x.float(), w.half().float().to(DEV), b.to(DEV)) + res.float()
     close(y, ref, "persistent")
+
+
+@pytest.mark.parametrize("kind", ["linear_res", "linear_res_aux", "conv_res", "geglu"])
+def test_epilogue_is_bit_reproducible(kind):
+    """The kernel has no atomics and a fixed summation order, so a launch repeated on the same operands must be bit-identical.
+    This is the race detector for the epilogue's shared-memory rings: without the proxy fence between the generic-proxy reads of
+    a residual slot and its next TMA overwrite, 1-3 % of launches of these layer classes (odd chunk counts per tile, full-size M)
+    picked up a few 16-byte pieces of another chunk's residual (scripts/stress_gemm_res3.py)."""
+    reps = 150
+    if kind in ("linear_res", "linear_res_aux"):
+        m, k, n = 258048, 1280, 320                                  # bn = 160: 5 chunks per tile
+        x = rnd(m, k, seed=1).half().to(DEV)
+        gw = ops.prep_linear(rnd(n, k, seed=2, scale=k ** -0.5), rnd(n, seed=3), DEV)
+        res = rnd(m, n, seed=4).half().to(DEV)
+        aux = rnd(m, n, seed=5).half().to(DEV) if kind == "linear_res_aux" else None
+        out = torch.empty(m, n, device=DEV, dtype=torch.half)
+        fn = (lambda: ops.linear(x, gw, res=res, out=out)) if aux is None else \
+             (lambda: ops.linear(x, gw, res=res, aux=aux, s_acc=0.7, s_res=0.7, s_aux=0.3, out=out))
+    elif kind == "conv_res":
+        x = rnd(28, 72, 128, 320, seed=1).half().to(DEV)
+        gw = ops.prep_conv(rnd(320, 320, 3, 3, seed=2, scale=0.02), rnd(320, seed=3), DEV)
+        res = rnd(28, 72, 128, 320, seed=4).half().to(DEV)
+        out = torch.empty(28, 72, 128, 320, device=DEV, dtype=torch.half)
+        fn = lambda: ops.conv3x3(x, gw, res=res, out=out)
+    else:
+        m, c = 64512, 640
+        x = rnd(m, c, seed=1).half().to(DEV)
+        gw = ops.prep_linear(rnd(8 * c, c, seed=2, scale=c ** -0.5), rnd(8 * c, seed=3), DEV, geglu=True)
+        out = torch.empty(m, 4 * c, device=DEV, dtype=torch.half)
+        fn = lambda: ops.linear(x, gw, out=out)
+    ref = fn().clone()
+    bad = sum(0 if torch.equal(fn(), ref) else 1 for _ in range(reps))
+    assert bad == 0, f"{kind}: {bad}/{reps} repeated launches differ from the first"

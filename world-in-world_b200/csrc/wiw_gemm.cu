@@ -137,21 +137,23 @@ __device__ __forceinline__ void lean_geglu(f32x2 (&v)[kEpiPairs], const uint32_t
         }
     }
 }
-// residual chunk n of this CTA sits in slot n % 4 (phase bit (n / 4) & 1), written by the loader warp
-__device__ __forceinline__ void lean_residual(f32x2 (&v)[kEpiPairs], const uint8_t* slots_row, uint32_t n, uint32_t bar_rfull,
-                                              uint32_t bar_rempty, float s_res, uint32_t sw) {
-    const uint32_t rs = n & 3u;
-    mbar_wait(bar_rfull + 8 * rs, (n >> 2) & 1u);
+// the group's k-th residual chunk sits in its own two-slot ring (lean kernels run with 4 slots): slot grp * 2 + (k & 1), phase (k >> 1) & 1
+__device__ __forceinline__ uint32_t lean_residual_load(uint4 (&u)[4], const uint8_t* slots_row, uint32_t grp, uint32_t k, uint32_t bar_rfull, uint32_t sw) {
+    const uint32_t rs = grp * 2u + (k & 1u);
+    mbar_wait(bar_rfull + 8 * rs, (k >> 1) & 1u);
     const uint8_t* p = slots_row + rs * kEpiChunkBytes;
+#pragma unroll
+    for (int c4 = 0; c4 < 4; ++c4) u[c4] = *reinterpret_cast<const uint4*>(p + ((uint32_t(c4) ^ sw) << 4));
+    return rs;
+}
+__device__ __forceinline__ void lean_residual_add(f32x2 (&v)[kEpiPairs], const uint4 (&u)[4], float s_res) {
     const f32x2 s2 = pk2(s_res, s_res);
 #pragma unroll
     for (int c4 = 0; c4 < 4; ++c4) {
-        const uint4 u = *reinterpret_cast<const uint4*>(p + ((uint32_t(c4) ^ sw) << 4));
-        const __half2* h = reinterpret_cast<const __half2*>(&u);
+        const __half2* h = reinterpret_cast<const __half2*>(&u[c4]);
 #pragma unroll
         for (int e = 0; e < 4; ++e) v[c4 * 4 + e] = fma2(s2, half2_to_f32x2(h[e]), v[c4 * 4 + e]);
     }
-    mbar_arrive(bar_rempty + 8 * rs);
 }
 __device__ __forceinline__ void lean_stage(uint8_t* p, const f32x2 (&v)[kEpiPairs], uint32_t sw) {
 #pragma unroll
@@ -343,13 +345,22 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         if (has_epi_loads) {
             const int full_chunks = g.out_cols_per_tile / kEpiCols;
             const uint32_t bytes = kEpiChunkBytes * ((g.has_res ? 1 : 0) + (g.has_aux ? 1 : 0));
-            int rs = 0;
-            uint32_t rph = 0;
+            // Each epilogue group owns HALF of the slots as its own ring (group of chunk j = j & 1; the group's k-th chunk sits in its
+            // slot k % per, phase (k / per) & 1).  With one ring shared by both groups, consecutive uses of a slot could belong to
+            // different groups (odd chunk counts per tile): a group that ran ahead then waited on the slot's barrier one phase early,
+            // the parity test passed on the phase before, and it read the slot before its data had landed (seen as rare wrong residual
+            // values once the epilogue got faster; scripts/stress_gemm_res.py).  One consumer group per slot makes its uses ordered.
+            const uint32_t per = uint32_t(g.res_slots) >> 1, per_shift = (per == 4u) ? 2u : 1u;
+            uint32_t cnt[2] = {0u, 0u};
             for (int tile = first_tile; tile < g.total_tiles; tile += tile_step) {
                 const TileCoord t = decode_tile<CG>(g, tile, cta_rank);
                 const int c0 = t.n_tile * g.out_cols_per_tile;
                 const int chunks = min(full_chunks, (g.out_total - c0) / kEpiCols);     // the last N-tile may be ragged
                 for (int j = 0; j < chunks; ++j) {
+                    const uint32_t gsel = uint32_t(j) & 1u;
+                    const uint32_t k = gsel ? cnt[1]++ : cnt[0]++;
+                    const uint32_t rs = gsel * per + (k & (per - 1u));
+                    const uint32_t rph = (k >> per_shift) & 1u;
                     mbar_wait(bar_rempty + 8 * rs, rph ^ 1);
                     if (elect_one()) {
                         mbar_expect_tx(bar_rfull + 8 * rs, bytes);
@@ -357,7 +368,6 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                         if (g.has_aux) tma_load_4d(aux_base + rs * kEpiChunkBytes, &tm_aux, bar_rfull + 8 * rs, c0 + j * kEpiCols, t.x0, t.y0, t.img);
                     }
                     __syncwarp();
-                    if (++rs == g.res_slots) { rs = 0; rph ^= 1; }
                 }
             }
         }
@@ -386,7 +396,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         const float s_acc = g.s_acc;
         const bool e_sacc = s_acc != 1.0f;
         const int res_slots = LEAN ? 4 : g.res_slots;
-        const int res_shift = (res_slots == 8) ? 3 : 2;
+        const uint32_t res_per = uint32_t(res_slots) >> 1, res_per_shift = (res_per == 4u) ? 2u : 1u;       // this group's ring: slots grp * per ...
         const bool e_aux = !LEAN && g.has_aux;
         const bool e_res = g.has_res;
         const bool e_loads = e_res || e_aux;
@@ -395,7 +405,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         const bool e_bias = g.bias != nullptr;
         const float s_res = g.s_res;
         const int wx0 = g.wx0[q], wy0 = g.wy0[q], wz0 = g.wz0[q];
-        uint32_t chunk_base = 0;                       // chunks consumed by this CTA before the current tile (mod 2^32: only its low bits are used)
+        uint32_t res_k = 0;                            // residual / aux chunks this GROUP has consumed so far (its ring position, see the loader)
         int chunks = 0;
         const bool eprof = (e_dbg & 4) && blockIdx.x == 0 && warp == 4;
         long long e_wait = 0;
@@ -410,7 +420,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 #define EPH_BEGIN() do { } while (0)
 #endif
         const long long e_t0 = eprof ? clock64() : 0;
-        for (int tile = first_tile; tile < g.total_tiles; tile += tile_step, chunk_base += chunks) {
+        for (int tile = first_tile; tile < g.total_tiles; tile += tile_step) {
             const TileCoord t = decode_tile<CG>(g, tile, cta_rank);
             const int acc_n0 = t.n_tile * g.bn;                       // first GEMM column of this tile
             const int out_c0 = t.n_tile * g.out_cols_per_tile;        // first output channel
@@ -512,8 +522,18 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                     EPH(2);
                     if (e_res) {
                         const uint8_t* gen = smem_raw + (res_base - smem_u32(smem_raw)) + row_off;
-                        lean_residual(va, gen, chunk_base + uint32_t(j0), bar_rfull, bar_rempty, s_res, sw);
-                        if (two) lean_residual(vb, gen, chunk_base + uint32_t(j1), bar_rfull, bar_rempty, s_res, sw);
+                        uint4 ua[4], ub[4];
+                        const uint32_t rsa = lean_residual_load(ua, gen, uint32_t(grp), res_k++, bar_rfull, sw);
+                        uint32_t rsb = 0;
+                        if (two) rsb = lean_residual_load(ub, gen, uint32_t(grp), res_k++, bar_rfull, sw);
+                        // The slots were read through the generic proxy and will be overwritten through the async proxy (the loader's next
+                        // TMA load): that order needs a proxy fence before the release.  Without it ~1-3 % of launches picked up a few
+                        // 16-byte pieces of the NEXT chunk's residual (scripts/stress_gemm_res3.py; the slower general epilogue hid it).
+                        fence_proxy_async_smem();
+                        mbar_arrive(bar_rempty + 8 * rsa);
+                        if (two) mbar_arrive(bar_rempty + 8 * rsb);
+                        lean_residual_add(va, ua, s_res);
+                        if (two) lean_residual_add(vb, ub, s_res);
                     }
                     EPH(3);
                     // both staging buffers of the group are rewritten: every earlier bulk store of this warp must have read its slab
@@ -628,9 +648,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 }
                 EPH(2);
                 if (e_loads) {
-                    const uint32_t n = chunk_base + uint32_t(j);              // global chunk index of this CTA (res_slots is 4 or 8: mask and shift, no division)
-                    const int rs = int(n & uint32_t(res_slots - 1));
-                    const uint32_t rph = (n >> res_shift) & 1u;
+                    const int rs = int(uint32_t(grp) * res_per + (res_k & (res_per - 1u)));
+                    const uint32_t rph = (res_k >> res_per_shift) & 1u;
+                    ++res_k;
                     mbar_wait(bar_rfull + 8 * rs, rph);
                     const uint8_t* gen = smem_raw + (res_base - smem_u32(smem_raw));
                     if (e_res) {
@@ -661,6 +681,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                             }
                         }
                     }
+                    fence_proxy_async_smem();                 // generic-proxy reads of the slot before its async-proxy (TMA) overwrite
                     mbar_arrive(bar_rempty + 8 * rs);
                 }
                 EPH(3);
