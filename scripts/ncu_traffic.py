@@ -56,7 +56,7 @@ def main():
     for r in data:
         d = {"kernel": r[ix["Kernel Name"]].split("(")[0].replace("void ", ""), "grid": r[ix["Grid Size"]] if "Grid Size" in ix else ""}
         for m, k in METRICS.items():
-            if m in ix and r[ix[m]] not in ("", "n/a"):
+            if m in ix and r[ix[m]] not in ("", "n/a", "no data"):
                 d[k] = to_bytes(r[ix[m]], units[ix[m]]) if k in ("rd", "wr") else float(r[ix[m]].replace(",", ""))
                 if k == "ns":
                     d[k] *= {"ns": 1, "us": 1e3, "usecond": 1e3, "ms": 1e6, "msecond": 1e6, "nsecond": 1, "second": 1e9}.get(units[ix[m]], 1)

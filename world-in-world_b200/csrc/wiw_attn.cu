@@ -16,6 +16,9 @@
 //              of O in TMEM when some row max of the warp grew by more than 2^8.  The row sum l is NOT accumulated by the
 //              softmax threads: the PV MMA runs with N = 80 where B columns 64..79 come from a tile of ones, so
 //              O[:, 64] = sum_k P[:, k] in fp32 for free.  Final O / l -> fp16 -> TMA store.
+// This kernel does not use setmaxnreg, so the mbarrier-timeout diagnostic may stay a real (noinline, printf) call: with the inline trap
+// the softmax loop scheduled measurably worse (profiles/r02_attn_trap_call_ab.txt).
+#define WIW_TRAP_PRINTF 1
 #include "wiw_common.cuh"
 #include "../../include/wiw.h"
 
