@@ -74,25 +74,60 @@ __device__ __forceinline__ void mask_chunk(uint32_t* r, int base, int valid) {
         if (base + e >= valid) r[e] = 0xff800000u;
 }
 
+// The softmax warps are bound by instruction issue inside their dependency chains, so the per-score work uses the
+// instructions that do two things at once: 3-input max (FMNMX3) for the row maximum, packed f32x2 FMA / ADD (FFMA2, FADD2: the pipe
+// time of two scalar instructions, the issue cost of one) for the scaling and the polynomial.  Same operations, same rounding: the
+// results are bit-identical to the scalar forms.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float a, float b) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ f32x2 pk2u(uint32_t a, uint32_t b) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(a), "r"(b)); return r; }
+__device__ __forceinline__ void upk2(f32x2 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ float max3(float a, float b, float c) { float d; asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c)); return d; }
+
 __device__ __forceinline__ float row_max_chunk(const uint32_t* r, float mx) {
 #pragma unroll
-    for (int e = 0; e < 32; e += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(r[e]), __uint_as_float(r[e + 1])));
+    for (int e = 0; e < 32; e += 2) mx = max3(mx, __uint_as_float(r[e]), __uint_as_float(r[e + 1]));
     return mx;
+}
+
+// exp2_poly on a pair (same clamp, split and polynomial; the exponent insertion stays scalar integer work)
+__device__ __forceinline__ void exp2_poly2(f32x2 x, float& y0, float& y1) {
+    float x0, x1;
+    upk2(x, x0, x1);
+    x = pk2(fmaxf(x0, -26.0f), fmaxf(x1, -26.0f));
+    const f32x2 xr = add2(x, pk2(12582912.0f, 12582912.0f));
+    const f32x2 f = fma2(add2(xr, pk2(-12582912.0f, -12582912.0f)), pk2(-1.0f, -1.0f), x);          // x - (xr - 1.5 * 2^23), in [-0.5, 0.5]
+    f32x2 p = fma2(pk2(0.05517167f, 0.05517167f), f, pk2(0.24261113f, 0.24261113f));
+    p = fma2(p, f, pk2(0.69326097f, 0.69326097f));
+    p = fma2(p, f, pk2(0.99992806f, 0.99992806f));
+    float p0, p1, r0, r1;
+    upk2(p, p0, p1);
+    upk2(xr, r0, r1);
+    y0 = __int_as_float(__float_as_int(p0) + (__float_as_int(r0) << 23));
+    y1 = __int_as_float(__float_as_int(p1) + (__float_as_int(r1) << 23));
 }
 
 // 32 scores -> 32 fp16 probabilities p = 2^(s*c - mc) written to the swizzled P tile
 // (fp32 MUFU.EX2 + one F2FP pack per pair: cheaper than ex2.f16x2, which splits into two MUFU + a PRMT)
 template <int kPolyPairs>
 __device__ __forceinline__ void exp_chunk(const uint32_t* r, int ch, float c, float mc, uint8_t* dst, uint32_t sw) {
+    const f32x2 c2 = pk2(c, c), nmc2 = pk2(-mc, -mc);
 #pragma unroll
     for (int v8 = 0; v8 < 4; ++v8) {
         uint32_t p[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-            const float a0 = fmaf(__uint_as_float(r[v8 * 8 + 2 * e]), c, -mc);
-            const float a1 = fmaf(__uint_as_float(r[v8 * 8 + 2 * e + 1]), c, -mc);
-            if (e < kPolyPairs) p[e] = cvt_f16x2(exp2_poly(a0), exp2_poly(a1));
-            else p[e] = cvt_f16x2(fast_exp2(a0), fast_exp2(a1));
+            const f32x2 a = fma2(pk2u(r[v8 * 8 + 2 * e], r[v8 * 8 + 2 * e + 1]), c2, nmc2);      // s * c - m * c, two scores per instruction
+            float y0, y1;
+            if (e < kPolyPairs) exp2_poly2(a, y0, y1);
+            else {
+                float a0, a1;
+                upk2(a, a0, a1);
+                y0 = fast_exp2(a0); y1 = fast_exp2(a1);
+            }
+            p[e] = cvt_f16x2(y0, y1);
         }
         const uint32_t chunk16 = (uint32_t)((ch & 1) * 4 + v8);
         *reinterpret_cast<uint4*>(dst + ((chunk16 ^ sw) << 4)) = make_uint4(p[0], p[1], p[2], p[3]);
@@ -365,14 +400,19 @@ extern "C" int wiw_attention_spatial(const void* qkv, void* out, int images, int
     a.scale_log2 = 0.125f * 1.4426950408889634f;
     static unsigned long long attr_set = 0;
     if (first_call_on_device(&attr_set)) {
+        WIW_CHECK_CUDA(cudaFuncSetAttribute(attn_spatial_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
         WIW_CHECK_CUDA(cudaFuncSetAttribute(attn_spatial_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
+        WIW_CHECK_CUDA(cudaFuncSetAttribute(attn_spatial_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
     }
-    // 1 of every 4 exponential pairs runs on the FMA pipe (exp2_poly): A/B on B200 +6 % at S = 9216 over all-MUFU, 2 of 4 is -4 %
-    // (profiles/r01_perf_attn_poly_ab_v7.txt).  Round 2 rebuilt this kernel six ways (A operands in tensor memory, P aliased on S,
+    static const int poly = getenv("WIW_ATTN_POLY") ? atoi(getenv("WIW_ATTN_POLY")) : 1;      // development aid for A/B runs
+    // 1 of every 4 exponential pairs runs on the FMA pipe (exp2_poly2): with the packed f32x2 softmax 898 TFLOP/s at S = 9216 against 782
+    // all-MUFU and 755 with 2 of 4 (profiles/r02_attn_poly_share_packed_ab.txt).  Round 2 rebuilt this kernel six ways (A operands in tensor memory, P aliased on S,
     // two / four threads per row, double-buffered scores, one MMA warp per Q tile): all are correct, none beats this one by more
     // than 2 % -- DESIGN.md section 4 and profiles/r02_attn_*.txt; the variants live in the git history (commits c837173..33a0137).
     dim3 grid((S + 2 * kQ - 1) / (2 * kQ), C / 64, images);
-    attn_spatial_kernel<1><<<grid, kAttnThreads, kAttnSmem, stream>>>(tm_qkv, tm_out, a, C);
+    if (poly == 0) attn_spatial_kernel<0><<<grid, kAttnThreads, kAttnSmem, stream>>>(tm_qkv, tm_out, a, C);
+    else if (poly == 2) attn_spatial_kernel<2><<<grid, kAttnThreads, kAttnSmem, stream>>>(tm_qkv, tm_out, a, C);
+    else attn_spatial_kernel<1><<<grid, kAttnThreads, kAttnSmem, stream>>>(tm_qkv, tm_out, a, C);
     WIW_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
