@@ -4,13 +4,15 @@
 //
 //   warp 0      TMA producer: per k-iteration one 5-D box load of A (a 128-pixel patch x 64 channels,
 //               shifted by the filter tap; out-of-range = zero padding) and one 2-D box of W
-//   warp 1      MMA issuer: tcgen05.mma cta_group::1 kind::f16, M=128, N=bn, K=16 x4 per stage,
-//               fp32 accumulators in TMEM, double-buffered across tiles
-//   warp 2      TMEM allocator + TMA loader of the epilogue's residual / aux tiles
-//   warps 3-10  epilogue, two groups of 4 warps on alternating 32-column chunks: tcgen05.ld -> (bias,
+//   warp 1      MMA issuer: tcgen05.mma kind::f16, M=128 (cta_group::1) or M=256 over a CTA pair (cta_group::2), N=bn,
+//               K=16 x4 per stage, fp32 accumulators in TMEM, double-buffered across tiles
+//   warp 2      TMEM allocator + TMA loader of the epilogue's residual / aux tiles (one slot ring per epilogue group)
+//   warp 3      idle (completes warpgroup 0, which gives its registers away: setmaxnreg 40; the epilogue warps take 232)
+//   warps 4-11  epilogue, two groups of 4 warps on alternating 32-column chunks: tcgen05.ld -> (bias,
 //               per-row-group table, SiLU, GEGLU, residual blend) -> fp16 -> swizzled smem -> TMA store
 //               (clips partial tiles).  Every warp stages and stores its OWN 32-row slab (2 KB, its own
-//               bulk-store groups), so the epilogue warps never meet at a CTA barrier.
+//               bulk-store groups), so the epilogue warps never meet at a CTA barrier.  LEAN = 1 (no activation / aux):
+//               two chunks in flight per warp, packed f32x2 arithmetic, bias from a per-group shared-memory copy.
 //
 // Pipelines: smem full/empty ring (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue),
 // residual full/empty ring (loader <-> epilogue), bulk-group ring for the stores.
