@@ -136,3 +136,36 @@ def test_library_contains_native_tcgen05_and_tma_code():
         assert mnemonic in sass, f"{mnemonic} missing from the library's SASS"
     for kernel in ("conv_gemm_kernel", "attn_spatial_kernel", "temporal_attn_mma_kernel", "layernorm_lpr_kernel", "gn_apply_kernel"):
         assert kernel in sass
+
+
+def test_gemm_register_budgets_survive_the_compiler():
+    """conv_gemm_kernel rebalances registers by role with setmaxnreg (producers 40, epilogue 232).  A function CALL anywhere in the
+    kernel (a printf, a noinline helper) makes ptxas drop the per-role budgets and allocate everything under the smallest one:
+    nothing fails, the epilogue just spills ~1 KB per thread and the K <= 640 layers run up to 2x slower.
+    Guard: the lean kernels keep their USETMAXREG pair, contain no call and no local-memory traffic, and use the packed f32x2
+    forms the issue-bound epilogue is written around."""
+    import re
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([cuobjdump, "-sass", L.LIB_PATH], capture_output=True, text=True, timeout=300).stdout
+    kernels, name = {}, None
+    for line in sass.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            name = m.group(1)
+            kernels[name] = []
+        elif name is not None and "/*" in line:
+            kernels[name].append(line)
+    lean = {k: v for k, v in kernels.items() if re.search(r"conv_gemm_kernelILi[12]ELi[02]ELi1E", k)}     # <CG, GEGLU, LEAN = 1>
+    assert len(lean) == 4, sorted(kernels)[:8]
+    for k, body in lean.items():
+        text = "\n".join(body)
+        assert "USETMAXREG.DEALLOC" in text and "USETMAXREG.TRY_ALLOC" in text, f"{k}: setmaxnreg pair missing"
+        assert not re.search(r"\b(STL|LDL)\b", text), f"{k}: local-memory spills in a lean GEMM kernel"
+        assert not re.search(r"\bCALL\.ABS|\bCALL\.REL(?!\.NOINC)", text), f"{k}: a real function call voids the setmaxnreg budgets"
+        assert re.search(r"\bFFMA2\b|\bFADD2\b", text), f"{k}: packed f32x2 arithmetic missing"
+    attn = [v for k, v in kernels.items() if "attn_spatial_kernel" in k]
+    assert attn and all(re.search(r"\bFMNMX3\b", "\n".join(v)) and re.search(r"\bFFMA2\b", "\n".join(v)) for v in attn)
